@@ -1,0 +1,78 @@
+"""Pins for the ebur128 / loudnorm restatement (no ffmpeg binary here: parity vs ffmpeg is unpinned;
+these are the external known answers of SURVEY.md section 4)."""
+import math
+
+import numpy as np
+
+from oracle import chain, cport
+
+
+def test_bs1770_48k_coefficient_table():
+    """ITU-R BS.1770-4 Table 1/2 (48 kHz)."""
+    _, _, (pb, pa, rb, ra) = chain.k_weighting(48000)
+    assert np.allclose(pb, [1.53512485958697, -2.69169618940638, 1.19839281085285], atol=1e-13)
+    assert np.allclose(pa, [1.0, -1.69065929318241, 0.73248077421585], atol=1e-13)
+    assert np.allclose(rb, [1.0, -2.0, 1.0])
+    assert np.allclose(ra, [1.0, -1.99004745483398, 0.99007225036621], atol=1e-13)
+
+
+def _sine(fs, secs, freq, dbfs, stereo=True):
+    t = np.arange(int(fs * secs)) / fs
+    s = np.round(32767 * 10 ** (dbfs / 20) * np.sin(2 * np.pi * freq * t)).astype(np.int16)
+    z = np.zeros_like(s)
+    return np.stack([s, s if stereo else z], axis=1)
+
+
+def test_ebu_3341_case1_stereo_1k_minus23():
+    assert abs(chain.integrated_loudness(_sine(48000, 20, 1000, -23.0), 48000) - (-23.0)) < 0.1
+
+
+def test_997hz_full_scale_mono_is_minus_3_01():
+    # ffmpeg's ebur128 is histogram-only: a steady tone reports its 0.1 LU bin centre (-3.05 for -3.01)
+    v = chain.integrated_loudness(_sine(48000, 10, 997, 0.0, stereo=False), 48000)
+    assert abs(v - (-3.01)) <= 0.05 and abs(v - (-3.05)) < 1e-9
+
+
+def test_relative_gate_ignores_quiet_passage():
+    loud = _sine(48000, 10, 1000, -20.0)
+    quiet = _sine(48000, 10, 1000, -45.0)   # > -70 LUFS absolute gate, < relative gate
+    both = np.concatenate([loud, quiet, loud])
+    # transition blocks pass the gate and pull ~0.07 LU; an ungated mean would sit near -21.7
+    assert abs(chain.integrated_loudness(both, 48000) - chain.integrated_loudness(loud, 48000)) < 0.1
+
+
+def test_silence_is_minus_inf_and_copied_through():
+    z = np.zeros((48000, 2), dtype=np.int16)
+    info = {}
+    out = chain.normalize(z, 48000, -14.0, info)
+    assert info["input_i"] == -math.inf and not info["normalized"]
+    assert np.array_equal(out, z)
+    short = _sine(48000, 0.3, 1000, -10.0)  # < 400 ms: no gating block at all
+    assert chain.integrated_loudness(short, 48000) == -math.inf
+
+
+def test_literal_df2_matches_lfilter_restatement():
+    b, a, _ = chain.k_weighting(44100)
+    x = _sine(44100, 1.0, 440, -6.0)
+    lit = cport.kfilter_df2(x, b, a)
+    assert np.max(np.abs(lit - chain.k_weighted(x, 44100, literal=False))) < 1e-9
+
+
+def test_independent_crosscheck_torchaudio():
+    """torchaudio's BS.1770 loudness (non-histogram) is an independent implementation."""
+    import torch
+    import torchaudio
+    from audio_mastering_engine_b200 import synth
+    x = synth.track(6.0, 48000, track_id=2)
+    ours = chain.integrated_loudness(x, 48000)
+    wav = torch.from_numpy(x.astype(np.float32).T / 32768.0)
+    theirs = float(torchaudio.functional.loudness(wav, 48000))
+    assert abs(ours - theirs) < 0.1
+
+
+def test_static_gain_rounding_and_apply():
+    g, mi = chain.static_gain_from_measured(-20.126, -14.0)
+    assert mi == -20.13 and g == math.pow(10.0, (-14.0 + 20.13) / 20.0)
+    x = np.array([[100, -100], [32767, -32768], [3, -3]], dtype=np.int16)
+    y = chain.apply_static_gain(x, 1.5)
+    assert y.tolist() == [[150, -150], [32767, -32768], [4, -4]]  # lrint: 4.5 -> 4 (half to even)
