@@ -28,6 +28,10 @@ def _maxdiff(a, b):
     return int(np.abs(a.astype(np.int32) - b.astype(np.int32)).max()) if a.size else 0
 
 
+def _lufs_close(a, b):
+    return a == b or abs(a - b) <= LUFS_TOL
+
+
 def _nz(a, b):
     return float(np.mean(a != b)) if a.size else 0.0
 
@@ -126,7 +130,7 @@ def test_master_vs_oracle(torch_cuda, fs, secs, chunk, settings_name):
         out, info = master(x, fs, settings, chunk_seconds=chunk, eq_tile_frames=tile, xover_tile_frames=tile,
                            kw_tile_subblocks=0 if tile == 0 else 3)
         ref, rinfo = chain.master(x, fs, settings, chunk_seconds=chunk)
-        assert abs(info["input_i"] - rinfo["input_i"]) <= LUFS_TOL
+        assert _lufs_close(info["input_i"], rinfo["input_i"])
         assert info["measured_i_2dp"] == rinfo["measured_i_2dp"]
         assert info["n_blocks"] == rinfo["n_blocks"]
         d = _maxdiff(out, ref)
