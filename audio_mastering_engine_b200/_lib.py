@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libame.so")
 
 AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE = 1, 2, 4, 8
+AME_N_KERNELS = 10
 AME_EQ_BYPASS, AME_EQ_SHELF_BOOST, AME_EQ_SHELF_CUT, AME_EQ_PEAK = 0, 1, 2, 3
 
 
@@ -66,6 +67,9 @@ SYMBOLS = {
     "ame_plan_total_frames": (C.c_int64, [C.c_void_p]),
     "ame_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "ame_plan_launch_count": (C.c_int64, [C.c_void_p]),
+    "ame_plan_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ame_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "ame_kernel_name": (C.c_char_p, [C.c_int]),
     "ame_master_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult), C.c_void_p]),
     "ame_master_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     "ame_measure_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

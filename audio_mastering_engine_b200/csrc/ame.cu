@@ -86,7 +86,28 @@ struct ame_plan {
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
     cudaStream_t io_stream = nullptr;
+    // optional per-kernel CUDA-event timing (ame_plan_set_timing)
+    bool timing = false;
+    int t_step = -1;
+    std::vector<cudaEvent_t> t_ev;        // [kMaxTimedSteps][AME_N_KERNELS][2]
+    std::vector<char> t_used;             // [kMaxTimedSteps][AME_N_KERNELS]
 };
+
+constexpr int kMaxTimedSteps = 64;
+static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_rms", "k_att_chain",
+    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
+enum { S_EQ = 0, S_SPLIT, S_RMS, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+
+static inline void t_begin(ame_plan *p, int slot, cudaStream_t s) {
+    if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps)
+        cudaEventRecord(p->t_ev[((size_t)p->t_step * AME_N_KERNELS + slot) * 2], s);
+}
+static inline void t_end(ame_plan *p, int slot, cudaStream_t s) {
+    if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps) {
+        cudaEventRecord(p->t_ev[((size_t)p->t_step * AME_N_KERNELS + slot) * 2 + 1], s);
+        p->t_used[(size_t)p->t_step * AME_N_KERNELS + slot] = 1;
+    }
+}
 
 namespace {
 
@@ -159,6 +180,7 @@ void ame_plan_destroy(ame_plan *p) {
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->io_stream) cudaStreamDestroy(p->io_stream);
+    for (cudaEvent_t e : p->t_ev) cudaEventDestroy(e);
     delete p;
 }
 
@@ -404,8 +426,10 @@ int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     if (p->n_eq_jobs) {
         const int threads = 128, blocks = (p->n_eq_jobs * 2 + threads - 1) / threads;
+        t_begin(p, S_EQ, s);
         k_eq<<<blocks, threads, 0, s>>>(p->d_eq_jobs, p->n_eq_jobs, p->d_tracks, p->d_luts, d_in, d_pre);
         LAUNCH_CHECK(p);
+        t_end(p, S_EQ, s);
     }
     return AME_OK;
 }
@@ -417,8 +441,10 @@ int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, vo
     if (p->n_split_jobs) {
         if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
         const int threads = 128, blocks = (p->n_split_jobs * 2 + threads - 1) / threads;
+        t_begin(p, S_SPLIT, s);
         k_band_split<<<blocks, threads, 0, s>>>(p->d_split_jobs, p->n_split_jobs, p->d_tracks, p->d_mb_delta, d_pre, d_bands, p->mb_frames);
         LAUNCH_CHECK(p);
+        t_end(p, S_SPLIT, s);
     }
     return AME_OK;
 }
@@ -430,14 +456,20 @@ int ame_stage_compress(ame_plan *p, const int16_t *d_bands, int16_t *d_pre, void
     if (!p->n_mb_chunks) return AME_OK;
     if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
     const size_t smem = (size_t)(p->max_look + kRmsTile) * 8;
-    k_window_rms<<<p->n_rms_jobs, kRmsThreads, smem, s>>>(p->d_rms_jobs, p->d_mb_chunks, p->d_tracks, d_bands, p->d_rms, p->mb_frames, p->max_look);
+    t_begin(p, S_RMS, s);
+        k_window_rms<<<p->n_rms_jobs, kRmsThreads, smem, s>>>(p->d_rms_jobs, p->d_mb_chunks, p->d_tracks, d_bands, p->d_rms, p->mb_frames, p->max_look);
     LAUNCH_CHECK(p);
-    k_att_chain<<<(p->n_chain_jobs + 31) / 32, 32, 0, s>>>(p->d_chain_jobs, p->n_chain_jobs, p->d_rms, p->d_tables, p->d_ckpt, p->mb_frames, p->n_seg_total);
+        t_end(p, S_RMS, s);
+    t_begin(p, S_CHAIN, s);
+        k_att_chain<<<(p->n_chain_jobs + 31) / 32, 32, 0, s>>>(p->d_chain_jobs, p->n_chain_jobs, p->d_rms, p->d_tables, p->d_ckpt, p->mb_frames, p->n_seg_total);
     LAUNCH_CHECK(p);
+        t_end(p, S_CHAIN, s);
     const int threads = 128;
     const int blocks = (int)((p->n_seg_total + threads - 1) / threads);
-    k_compress_apply<<<blocks, threads, 0, s>>>(p->d_mb_chunks, p->n_mb_chunks, p->n_seg_total, p->d_tracks, d_bands, p->d_rms, p->d_tables, p->d_ckpt, d_pre, p->mb_frames);
+    t_begin(p, S_APPLY, s);
+        k_compress_apply<<<blocks, threads, 0, s>>>(p->d_mb_chunks, p->n_mb_chunks, p->n_seg_total, p->d_tracks, d_bands, p->d_rms, p->d_tables, p->d_ckpt, d_pre, p->mb_frames);
     LAUNCH_CHECK(p);
+        t_end(p, S_APPLY, s);
     return AME_OK;
 }
 
@@ -448,13 +480,19 @@ int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, 
     CU(cudaMemsetAsync(p->d_peak, 0, (size_t)p->n_tracks * 4, s));
     if (p->n_kw_jobs) {
         const int threads = 128, blocks = (p->n_kw_jobs * 2 + threads - 1) / threads;
+        t_begin(p, S_KW, s);
         k_kweight_energy<<<blocks, threads, 0, s>>>(p->d_kw_jobs, p->n_kw_jobs, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
         LAUNCH_CHECK(p);
+        t_end(p, S_KW, s);
     }
-    k_tail_peak<<<p->n_tracks, 128, 0, s>>>(p->d_tracks, p->d_tdev, p->n_tracks, d_pre, p->d_peak);
+    t_begin(p, S_TAIL, s);
+        k_tail_peak<<<p->n_tracks, 128, 0, s>>>(p->d_tracks, p->d_tdev, p->n_tracks, d_pre, p->d_peak);
     LAUNCH_CHECK(p);
-    k_block_hist<<<p->n_tracks, 256, 0, s>>>(p->d_tdev, p->d_energy, (long long *)d_hist);
+        t_end(p, S_TAIL, s);
+    t_begin(p, S_HIST, s);
+        k_block_hist<<<p->n_tracks, 256, 0, s>>>(p->d_tdev, p->d_energy, (long long *)d_hist);
     LAUNCH_CHECK(p);
+        t_end(p, S_HIST, s);
     return AME_OK;
 }
 
@@ -463,11 +501,15 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
     if (!p || !d_pre || !d_hist || !d_out) return fail(AME_E_INVALID, "NULL argument");
     CU(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_finalize<<<(p->n_tracks + 63) / 64, 64, 0, s>>>(p->d_tracks, p->n_tracks, (const long long *)d_hist, p->d_peak, p->d_results);
+    t_begin(p, S_FIN, s);
+        k_finalize<<<(p->n_tracks + 63) / 64, 64, 0, s>>>(p->d_tracks, p->n_tracks, (const long long *)d_hist, p->d_peak, p->d_results);
     LAUNCH_CHECK(p);
+        t_end(p, S_FIN, s);
     if (p->n_gain_jobs) {
+        t_begin(p, S_GAIN, s);
         k_apply_gain<<<p->n_gain_jobs, 256, 0, s>>>(p->d_gain_jobs, p->d_results, d_pre, d_out);
         LAUNCH_CHECK(p);
+        t_end(p, S_GAIN, s);
     }
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
@@ -476,9 +518,43 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
     return AME_OK;
 }
 
+int ame_plan_set_timing(ame_plan *p, int enable) {
+    if (!p) return fail(AME_E_INVALID, "NULL plan");
+    CU(cudaSetDevice(p->device));
+    if (enable && p->t_ev.empty()) {
+        p->t_ev.resize((size_t)kMaxTimedSteps * AME_N_KERNELS * 2);
+        for (auto &e : p->t_ev) CU(cudaEventCreate(&e));
+    }
+    p->t_used.assign((size_t)kMaxTimedSteps * AME_N_KERNELS, 0);
+    p->t_step = -1;
+    p->timing = enable != 0;
+    return AME_OK;
+}
+
+int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n_steps) {
+    if (!p || !ms_sum || !launches) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    const int steps = std::min(p->t_step + 1, kMaxTimedSteps);
+    for (int k = 0; k < AME_N_KERNELS; ++k) { ms_sum[k] = 0; launches[k] = 0; }
+    for (int st = 0; st < steps; ++st)
+        for (int k = 0; k < AME_N_KERNELS; ++k)
+            if (!p->t_used.empty() && p->t_used[(size_t)st * AME_N_KERNELS + k]) {
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, p->t_ev[((size_t)st * AME_N_KERNELS + k) * 2], p->t_ev[((size_t)st * AME_N_KERNELS + k) * 2 + 1]));
+                ms_sum[k] += ms;
+                ++launches[k];
+            }
+    if (n_steps) *n_steps = steps;
+    return AME_OK;
+}
+
+const char *ame_kernel_name(int slot) { return (slot >= 0 && slot < AME_N_KERNELS) ? kKernelNames[slot] : ""; }
+
 int ame_measure_device(ame_plan *p, const int16_t *d_in, int64_t *d_hist, void *stream) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
     p->launches = 0;
+    if (p->timing) ++p->t_step;
     int rc;
     if ((rc = ame_stage_eq(p, d_in, p->d_pre, stream))) return rc;
     if ((rc = ame_stage_band_split(p, p->d_pre, p->d_bands, stream))) return rc;

@@ -143,6 +143,18 @@ class MasterPlan:
         L.check(self.lib.ame_normalize_device(self.handle, self._ptr(d_hist), self._ptr(d_out), res, C.c_void_p(stream or 0)))
         return self.results() if fetch_results else None
 
+    def set_timing(self, enable=True):
+        L.check(self.lib.ame_plan_set_timing(self.handle, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{kernel name: (summed ms, launches)} and the number of recorded steps since set_timing()."""
+        ms = (C.c_double * L.AME_N_KERNELS)()
+        cnt = (C.c_int64 * L.AME_N_KERNELS)()
+        steps = C.c_int(0)
+        L.check(self.lib.ame_plan_kernel_times(self.handle, ms, cnt, C.byref(steps)))
+        names = [self.lib.ame_kernel_name(i).decode() for i in range(L.AME_N_KERNELS)]
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}, steps.value
+
     # stage entry points (parity taps)
     def stage_eq(self, d_in, d_pre, stream=None):
         L.check(self.lib.ame_stage_eq(self.handle, self._ptr(d_in), self._ptr(d_pre), C.c_void_p(stream or 0)))

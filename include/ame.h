@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define AME_ABI_VERSION 1
+#define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
     AME_OK = 0,
@@ -137,6 +138,12 @@ int ame_plan_set_warm_luts(ame_plan *plan, const float *luts, int32_t n_luts);
 int64_t ame_plan_total_frames(const ame_plan *plan);     /* padded length of the packed buffers */
 size_t ame_plan_workspace_bytes(const ame_plan *plan);
 int64_t ame_plan_launch_count(const ame_plan *plan);      /* kernels launched by the last call */
+
+/* per-kernel device timing with CUDA events on the processing stream (benchmarks): enable, run up to 64
+ * ame_master_* / ame_measure_* calls, then read the summed milliseconds and launch counts per kernel. */
+int ame_plan_set_timing(ame_plan *plan, int enable);
+int ame_plan_kernel_times(ame_plan *plan, double *ms_sum, int64_t *launches, int *n_steps);
+const char *ame_kernel_name(int slot);
 
 /* the whole path: replaces the chunk loop + concat + loudnorm of
  * process_audio_with_ffmpeg_pipeline (:185-220).  d_in / d_out are DEVICE pointers to packed
