@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libame.so")
 
 AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE = 1, 2, 4, 8
-AME_N_KERNELS = 10
+AME_N_KERNELS = 9
 AME_EQ_BYPASS, AME_EQ_SHELF_BOOST, AME_EQ_SHELF_CUT, AME_EQ_PEAK = 0, 1, 2, 3
 
 
@@ -81,7 +81,6 @@ SYMBOLS = {
     "ame_stage_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult), C.c_void_p]),
     "ame_plan_tap_pre": (C.c_void_p, [C.c_void_p]),
     "ame_plan_tap_bands": (C.c_void_p, [C.c_void_p]),
-    "ame_plan_tap_rms": (C.c_void_p, [C.c_void_p]),
     "ame_plan_tap_subblock_energy": (C.c_void_p, [C.c_void_p]),
     "ame_plan_mb_frames": (C.c_int64, [C.c_void_p]),
     "ame_plan_mb_offset": (C.c_int64, [C.c_void_p, C.c_int32]),

@@ -58,10 +58,10 @@ struct ame_plan {
     std::vector<TrackDev> tdev;
     int64_t total_frames = 0;             // padded
     int64_t mb_frames = 0;                // padded
-    int64_t n_seg_total = 0;
     int64_t n_sb_total = 0;
     int max_look = 0;
-    int n_eq_jobs = 0, n_split_jobs = 0, n_rms_jobs = 0, n_chain_jobs = 0, n_mb_chunks = 0, n_kw_jobs = 0, n_gain_jobs = 0;
+    int n_eq_jobs = 0, n_split_jobs = 0, n_chain_jobs = 0, n_sum_jobs = 0, n_kw_jobs = 0, n_gain_jobs = 0;
+    int ring_size = 0, eq_slots = 0, split_slots = 0;
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     size_t ws_bytes = 0;
     int64_t launches = 0;
@@ -71,17 +71,15 @@ struct ame_plan {
     TrackDev *d_tdev = nullptr;
     int64_t *d_mb_delta = nullptr;
     TileJob *d_eq_jobs = nullptr, *d_split_jobs = nullptr;
-    MbChunk *d_mb_chunks = nullptr;
-    RmsJob *d_rms_jobs = nullptr;
     ChainJob *d_chain_jobs = nullptr;
+    SumJob *d_sum_jobs = nullptr;
     KwJob *d_kw_jobs = nullptr;
     GainJob *d_gain_jobs = nullptr;
     AttEntry *d_tables = nullptr;
-    float *d_luts = nullptr;
+    double *d_luts = nullptr;
     int n_luts = 0;
     int16_t *d_pre = nullptr, *d_bands = nullptr, *d_in = nullptr, *d_out = nullptr;
-    uint16_t *d_rms = nullptr;
-    double *d_ckpt = nullptr, *d_energy = nullptr;
+    double *d_energy = nullptr;
     long long *d_hist = nullptr;
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
@@ -94,9 +92,9 @@ struct ame_plan {
 };
 
 constexpr int kMaxTimedSteps = 64;
-static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_rms", "k_att_chain",
-    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
-enum { S_EQ = 0, S_SPLIT, S_RMS, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_compress", "k_band_sum",
+    "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
+enum { S_EQ = 0, S_SPLIT, S_COMP, S_SUM, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
 
 static inline void t_begin(ame_plan *p, int slot, cudaStream_t s) {
     if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps)
@@ -120,15 +118,51 @@ int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
     return AME_OK;
 }
 
+// split chunk [cb, ce) into ceil(n / T) near-equal tiles whose interior boundaries are multiples of 4
 void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T) {
+    const int64_t n = ce - cb;
+    if (n <= 0) return;
+    const int64_t k = (n + T - 1) / T;
+    const int64_t t = align_up((n + k - 1) / k, 8);
     int64_t b = cb;
     while (b < ce) {
-        int64_t e = (b + T) & ~(int64_t)3;
-        if (e <= b) e = b + T;
+        int64_t e = (b + t) & ~(int64_t)3;
+        if (e <= b) e = b + t;
         if (e > ce) e = ce;
         out.push_back(TileJob{cb, b, e, track, variant});
         b = e;
     }
+}
+
+// pad a track's job list with empty jobs to a whole number of warps (16 lane pairs)
+void pad_jobs(std::vector<TileJob> &out, size_t track_first) {
+    if (out.size() == track_first) return;
+    TileJob d = out.back();
+    d.tile_begin = d.tile_end;
+    while ((out.size() - track_first) % 16) out.push_back(d);
+}
+
+// smallest tile (multiple of 8, >= min_tile) whose job count, padded per track, fits `slots` lane pairs
+int64_t pick_tile(const std::vector<std::vector<int64_t>> &chunks_per_track, int64_t slots, int64_t min_tile) {
+    auto count = [&](int64_t T) {
+        int64_t jobs = 0;
+        for (const auto &cs : chunks_per_track) {
+            int64_t j = 0;
+            for (int64_t n : cs) j += (n + T - 1) / T;
+            jobs += align_up(j, 16);
+        }
+        return jobs;
+    };
+    int64_t lo = min_tile, hi = min_tile;
+    for (const auto &cs : chunks_per_track)
+        for (int64_t n : cs) hi = std::max(hi, align_up(n, 8));
+    if (count(lo) <= slots) return lo;
+    while (lo < hi) {                    // count() is non-increasing in T
+        const int64_t mid = align_up((lo + hi) / 2, 8);
+        if (mid >= hi) break;
+        if (count(mid) <= slots) hi = mid; else lo = mid + 8;
+    }
+    return hi;
 }
 
 int validate(const ame_track_params &t, int idx) {
@@ -145,6 +179,21 @@ int validate(const ame_track_params &t, int idx) {
         if (shelf ? (k != AME_EQ_SHELF_BOOST && k != AME_EQ_SHELF_CUT) : (k != AME_EQ_PEAK))
             return fail(AME_E_INVALID, "track %d: eq stage %d has kind %d", idx, s, k);
     }
+    // the kernels rely on the Butterworth numerator shape b0 * (1 +- 2 z^-1 + z^-2) that scipy.signal.butter
+    // produces for every filter of the reference (sign pattern and unit-gain sections are fixed by design)
+    auto shape = [&](const ame_biquad &q, double sgn, bool unit) {
+        return q.b1 == sgn * 2.0 * q.b0 && q.b2 == q.b0 && (!unit || q.b0 == 1.0);
+    };
+    bool ok = true;
+    if (t.eq[0].kind != AME_EQ_BYPASS) ok = ok && shape(t.eq[0].s[0], 1, false);
+    if (t.eq[3].kind != AME_EQ_BYPASS) ok = ok && shape(t.eq[3].s[0], -1, false);
+    for (int s = 1; s <= 2; ++s)
+        if (t.eq[s].kind != AME_EQ_BYPASS)
+            ok = ok && shape(t.eq[s].s[0], 1, false) && shape(t.eq[s].s[1], 1, true) && shape(t.eq[s].s[2], -1, true) &&
+                 shape(t.eq[s].s[3], -1, true);
+    if (t.flags & AME_F_MULTIBAND)
+        ok = ok && shape(t.xlp[0], 1, false) && shape(t.xlp[1], 1, true) && shape(t.xhp[0], -1, false) && shape(t.xhp[1], -1, true);
+    if (!ok) return fail(AME_E_UNSUPPORTED, "track %d: a filter section is not of Butterworth shape b0*(1 +- 2z^-1 + z^-2)", idx);
     if (t.flags & AME_F_MULTIBAND)
         for (int b = 0; b < 3; ++b) {
             const ame_comp_band &c = t.comp[b];
@@ -174,9 +223,9 @@ int ame_device_count(int *count) {
 void ame_plan_destroy(ame_plan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_mb_chunks, p->d_rms_jobs,
+    void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_sum_jobs,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
-                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_energy, p->d_hist, p->d_peak, p->d_results};
+                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_peak, p->d_results};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->io_stream) cudaStreamDestroy(p->io_stream);
@@ -232,23 +281,34 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         if (spans[i].first < align_up(spans[i - 1].second, 8)) return bail(fail(AME_E_INVALID, "tracks overlap in the packed buffer"));
     if (p->total_frames == 0) p->total_frames = 8;
 
-    // ---- tile sizes ---------------------------------------------------------------------------
-    auto auto_tile = [](int64_t frames, int requested) {
-        if (requested > 0) return (int)align_up(requested, 8);
-        int64_t T = (frames + kTargetPairs - 1) / kTargetPairs;
-        T = std::max<int64_t>(T, 512);
-        return (int)align_up(T, 8);
-    };
-    p->eq_tile = auto_tile(sum_frames, o.eq_tile_frames);
-    p->split_tile = auto_tile(sum_mb, o.xover_tile_frames);
+    // ---- chunk geometry -----------------------------------------------------------------------
+    std::vector<std::vector<int64_t>> chunks_all(n_tracks), chunks_mb;
+    for (int t = 0; t < n_tracks; ++t) {
+        const ame_track_params &tp = p->tracks[t];
+        const int64_t cf = tp.chunk_frames > 0 ? tp.chunk_frames : std::max<int64_t>(tp.n_frames, 1);
+        for (int64_t c0 = 0; c0 < tp.n_frames; c0 += cf) chunks_all[t].push_back(std::min(cf, tp.n_frames - c0));
+        if (tp.flags & AME_F_MULTIBAND) chunks_mb.push_back(chunks_all[t]);
+    }
+
+    // ---- tile sizes: ONE wave of resident lane pairs (no tail wave), else the minimum tile ---------
+    int n_sm = 148, occ_eq = 2, occ_split = 4;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
+    p->eq_slots = n_sm * std::max(occ_eq, 1) * 64;
+    p->split_slots = n_sm * std::max(occ_split, 1) * 64;
+    constexpr int64_t kMinTile = 512;
+    p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)pick_tile(chunks_all, p->eq_slots, kMinTile);
+    p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8)
+                                            : (int)pick_tile(chunks_mb, p->split_slots, kMinTile);
+    const int64_t kw_slots = (int64_t)n_sm * 16 * 64;
     if (o.kw_tile_subblocks > 0) p->kw_tile_sb = o.kw_tile_subblocks;
-    else p->kw_tile_sb = (int)std::max<int64_t>(1, (p->n_sb_total + kTargetPairs - 1) / kTargetPairs);
+    else p->kw_tile_sb = (int)std::max<int64_t>(1, (p->n_sb_total + kw_slots - 1) / kw_slots);
 
     // ---- job tables ---------------------------------------------------------------------------
     std::vector<TileJob> eq_jobs, split_jobs;
-    std::vector<MbChunk> mb_chunks;
-    std::vector<RmsJob> rms_jobs;
     std::vector<ChainJob> chain_jobs;
+    std::vector<SumJob> sum_jobs;
     std::vector<KwJob> kw_jobs;
     std::vector<GainJob> gain_jobs;
     std::vector<int64_t> mb_delta(n_tracks, 0);
@@ -260,6 +320,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         int variant = 0;
         for (int s = 0; s < 4; ++s)
             if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
+        if (tp.flags & AME_F_WARMTH) variant |= 16;
         const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
         if (mb) {
             mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
@@ -293,52 +354,51 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                 }
             }
         }
-        const int64_t cf = tp.chunk_frames > 0 ? tp.chunk_frames : std::max<int64_t>(tp.n_frames, 1);
-        for (int64_t c0 = 0; c0 < tp.n_frames; c0 += cf) {
-            const int64_t c1 = std::min(c0 + cf, tp.n_frames);
-            const int64_t cb = tp.offset_frames + c0, ce = tp.offset_frames + c1;
+        const size_t eq_first = eq_jobs.size(), split_first = split_jobs.size();
+        int64_t c0 = 0;
+        for (int64_t cn : chunks_all[t]) {
+            const int64_t cb = tp.offset_frames + c0, ce = cb + cn;
             tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
             if (mb) {
                 tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
-                MbChunk ck{cb, p->mb_offset[t] + c0, c1 - c0, p->n_seg_total, t, 0};
-                const int chunk_idx = (int)mb_chunks.size();
-                mb_chunks.push_back(ck);
                 for (int b = 0; b < 3; ++b) {
-                    for (int64_t tb = 0; tb < ck.n; tb += kRmsTile) rms_jobs.push_back(RmsJob{chunk_idx, b, tb});
                     const double thr = tp.comp[b].thresh_rms;
                     const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
-                    chain_jobs.push_back(ChainJob{ck.mb_begin, ck.n, ck.seg_prefix, b, tp.comp[b].table, thr_i, 0});
+                    chain_jobs.push_back(ChainJob{p->mb_offset[t] + c0, cn, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
                 }
-                p->n_seg_total += (ck.n + kCK - 1) / kCK;
             }
+            c0 += cn;
         }
+        pad_jobs(eq_jobs, eq_first);
+        pad_jobs(split_jobs, split_first);
+        if (mb)
+            for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
+                sum_jobs.push_back(SumJob{p->mb_offset[t] + b, tp.offset_frames + b, std::min<int64_t>(kGainTile, tp.n_frames - b)});
         for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
             kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
         for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
             gain_jobs.push_back(GainJob{tp.offset_frames + b, tp.offset_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
     }
-    // chain jobs: order so that the 32 lanes of a warp carry chains of similar length
+    // longest chains first: the sequential compressor kernel is bounded by its slowest warp
     std::stable_sort(chain_jobs.begin(), chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
 
     p->n_eq_jobs = (int)eq_jobs.size();
     p->n_split_jobs = (int)split_jobs.size();
-    p->n_mb_chunks = (int)mb_chunks.size();
-    p->n_rms_jobs = (int)rms_jobs.size();
     p->n_chain_jobs = (int)chain_jobs.size();
+    p->n_sum_jobs = (int)sum_jobs.size();
     p->n_kw_jobs = (int)kw_jobs.size();
     p->n_gain_jobs = (int)gain_jobs.size();
+    p->ring_size = 128;
+    while (p->ring_size < p->max_look + 64) p->ring_size <<= 1;
 
     // ---- device state -------------------------------------------------------------------------
     if ((rc = upload(&p->d_tracks, p->tracks)) || (rc = upload(&p->d_tdev, p->tdev)) || (rc = upload(&p->d_mb_delta, mb_delta)) ||
         (rc = upload(&p->d_eq_jobs, eq_jobs)) || (rc = upload(&p->d_split_jobs, split_jobs)) ||
-        (rc = upload(&p->d_mb_chunks, mb_chunks)) || (rc = upload(&p->d_rms_jobs, rms_jobs)) ||
-        (rc = upload(&p->d_chain_jobs, chain_jobs)) || (rc = upload(&p->d_kw_jobs, kw_jobs)) ||
-        (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_tables, tables)))
+        (rc = upload(&p->d_chain_jobs, chain_jobs)) || (rc = upload(&p->d_sum_jobs, sum_jobs)) ||
+        (rc = upload(&p->d_kw_jobs, kw_jobs)) || (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_tables, tables)))
         return bail(rc);
     const size_t fb = (size_t)p->total_frames * 4;
     if ((rc = dmalloc(p, (void **)&p->d_pre, fb)) || (rc = dmalloc(p, (void **)&p->d_bands, (size_t)p->mb_frames * 4 * 3)) ||
-        (rc = dmalloc(p, (void **)&p->d_rms, (size_t)p->mb_frames * 2 * 3)) ||
-        (rc = dmalloc(p, (void **)&p->d_ckpt, (size_t)p->n_seg_total * 8 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_energy, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
@@ -350,6 +410,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             return bail(fail(AME_E_CUDA, "cudaStreamCreate failed"));
     }
     if (cudaMemset(p->d_pre, 0, fb) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
+    if (p->mb_frames && cudaMemset(p->d_bands, 0, (size_t)p->mb_frames * 12) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
 
     // ebur128.c histogram tables (same libm calls as the C library)
     {
@@ -361,10 +422,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             cudaMemcpyToSymbol(c_hist_energy, energies, sizeof energies) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
-    if (p->max_look + kRmsTile > 0) {
-        const size_t smem = (size_t)(p->max_look + kRmsTile) * 8;
+    {
+        const size_t smem = (size_t)kCompWarps * p->ring_size * 8;
         if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(k_window_rms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            cudaFuncSetAttribute(k_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cannot reserve %zu bytes of shared memory", smem));
     }
     *out = p;
@@ -375,10 +436,12 @@ int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
     if (!p || !luts || n_luts <= 0) return fail(AME_E_INVALID, "bad warm lut arguments");
     CU(cudaSetDevice(p->device));
     if (p->d_luts) { cudaFree(p->d_luts); p->d_luts = nullptr; }
-    const size_t bytes = (size_t)n_luts * 65536 * sizeof(float);
-    int rc = dmalloc(p, (void **)&p->d_luts, bytes);
+    // widened exactly to double on the host so the kernel needs no float->double conversion per sample
+    std::vector<double> wide((size_t)n_luts * 65536);
+    for (size_t i = 0; i < wide.size(); ++i) wide[i] = (double)luts[i];
+    int rc = dmalloc(p, (void **)&p->d_luts, wide.size() * sizeof(double));
     if (rc) return rc;
-    CU(cudaMemcpy(p->d_luts, luts, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_luts, wide.data(), wide.size() * sizeof(double), cudaMemcpyHostToDevice));
     p->n_luts = n_luts;
     return AME_OK;
 }
@@ -388,7 +451,6 @@ size_t ame_plan_workspace_bytes(const ame_plan *p) { return p ? p->ws_bytes : 0;
 int64_t ame_plan_launch_count(const ame_plan *p) { return p ? p->launches : 0; }
 const int16_t *ame_plan_tap_pre(const ame_plan *p) { return p->d_pre; }
 const int16_t *ame_plan_tap_bands(const ame_plan *p) { return p->d_bands; }
-const uint16_t *ame_plan_tap_rms(const ame_plan *p) { return p->d_rms; }
 const double *ame_plan_tap_subblock_energy(const ame_plan *p) { return p->d_energy; }
 int64_t ame_plan_mb_frames(const ame_plan *p) { return p->mb_frames; }
 int64_t ame_plan_mb_offset(const ame_plan *p, int32_t t) { return (t < 0 || t >= p->n_tracks) ? -1 : p->mb_offset[t]; }
@@ -449,27 +511,22 @@ int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, vo
     return AME_OK;
 }
 
-int ame_stage_compress(ame_plan *p, const int16_t *d_bands, int16_t *d_pre, void *stream) {
+int ame_stage_compress(ame_plan *p, int16_t *d_bands, int16_t *d_pre, void *stream) {
     if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
     CU(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if (!p->n_mb_chunks) return AME_OK;
+    if (!p->n_chain_jobs) return AME_OK;
     if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-    const size_t smem = (size_t)(p->max_look + kRmsTile) * 8;
-    t_begin(p, S_RMS, s);
-        k_window_rms<<<p->n_rms_jobs, kRmsThreads, smem, s>>>(p->d_rms_jobs, p->d_mb_chunks, p->d_tracks, d_bands, p->d_rms, p->mb_frames, p->max_look);
+    const size_t smem = (size_t)kCompWarps * p->ring_size * 8;
+    t_begin(p, S_COMP, s);
+    k_compress<<<(p->n_chain_jobs + kCompWarps - 1) / kCompWarps, kCompWarps * 32, smem, s>>>(
+        p->d_chain_jobs, p->n_chain_jobs, d_bands, p->d_tables, p->mb_frames, p->ring_size);
     LAUNCH_CHECK(p);
-        t_end(p, S_RMS, s);
-    t_begin(p, S_CHAIN, s);
-        k_att_chain<<<(p->n_chain_jobs + 31) / 32, 32, 0, s>>>(p->d_chain_jobs, p->n_chain_jobs, p->d_rms, p->d_tables, p->d_ckpt, p->mb_frames, p->n_seg_total);
+    t_end(p, S_COMP, s);
+    t_begin(p, S_SUM, s);
+    k_band_sum<<<p->n_sum_jobs, 256, 0, s>>>(p->d_sum_jobs, d_bands, d_pre, p->mb_frames);
     LAUNCH_CHECK(p);
-        t_end(p, S_CHAIN, s);
-    const int threads = 128;
-    const int blocks = (int)((p->n_seg_total + threads - 1) / threads);
-    t_begin(p, S_APPLY, s);
-        k_compress_apply<<<blocks, threads, 0, s>>>(p->d_mb_chunks, p->n_mb_chunks, p->n_seg_total, p->d_tracks, d_bands, p->d_rms, p->d_tables, p->d_ckpt, d_pre, p->mb_frames);
-    LAUNCH_CHECK(p);
-        t_end(p, S_APPLY, s);
+    t_end(p, S_SUM, s);
     return AME_OK;
 }
 
@@ -478,6 +535,7 @@ int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, 
     CU(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(p->d_peak, 0, (size_t)p->n_tracks * 4, s));
+    CU(cudaMemsetAsync(p->d_energy, 0, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8, s));
     if (p->n_kw_jobs) {
         const int threads = 128, blocks = (p->n_kw_jobs * 2 + threads - 1) / threads;
         t_begin(p, S_KW, s);

