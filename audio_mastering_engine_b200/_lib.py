@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libame.so")
 
 AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE = 1, 2, 4, 8
-AME_N_KERNELS = 9
+AME_N_KERNELS = 10
 AME_EQ_BYPASS, AME_EQ_SHELF_BOOST, AME_EQ_SHELF_CUT, AME_EQ_PEAK = 0, 1, 2, 3
 
 

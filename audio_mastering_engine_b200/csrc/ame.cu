@@ -60,8 +60,9 @@ struct ame_plan {
     int64_t mb_frames = 0;                // padded
     int64_t n_sb_total = 0;
     int max_look = 0;
-    int n_eq_jobs = 0, n_split_jobs = 0, n_chain_jobs = 0, n_sum_jobs = 0, n_kw_jobs = 0, n_gain_jobs = 0;
-    int ring_size = 0, eq_slots = 0, split_slots = 0;
+    int n_eq_jobs = 0, n_split_jobs = 0, n_chain_jobs = 0, n_wf_jobs = 0, n_mb_chunks = 0, n_kw_jobs = 0, n_gain_jobs = 0;
+    int eq_slots = 0, split_slots = 0;
+    int64_t n_seg_total = 0, n_group_total = 0;
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     size_t ws_bytes = 0;
     int64_t launches = 0;
@@ -72,14 +73,16 @@ struct ame_plan {
     int64_t *d_mb_delta = nullptr;
     TileJob *d_eq_jobs = nullptr, *d_split_jobs = nullptr;
     ChainJob *d_chain_jobs = nullptr;
-    SumJob *d_sum_jobs = nullptr;
+    WfJob *d_wf_jobs = nullptr;
+    MbChunk *d_mb_chunks = nullptr;
     KwJob *d_kw_jobs = nullptr;
     GainJob *d_gain_jobs = nullptr;
     AttEntry *d_tables = nullptr;
     double *d_luts = nullptr;
     int n_luts = 0;
     int16_t *d_pre = nullptr, *d_bands = nullptr, *d_in = nullptr, *d_out = nullptr;
-    double *d_energy = nullptr;
+    uint16_t *d_rms = nullptr;
+    double *d_ckpt = nullptr, *d_attf = nullptr, *d_energy = nullptr;
     long long *d_hist = nullptr;
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
@@ -92,9 +95,9 @@ struct ame_plan {
 };
 
 constexpr int kMaxTimedSteps = 64;
-static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_compress", "k_band_sum",
-    "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
-enum { S_EQ = 0, S_SPLIT, S_COMP, S_SUM, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_flag", "k_att_chain",
+    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
+enum { S_EQ = 0, S_SPLIT, S_FLAG, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
 
 static inline void t_begin(ame_plan *p, int slot, cudaStream_t s) {
     if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps)
@@ -223,9 +226,9 @@ int ame_device_count(int *count) {
 void ame_plan_destroy(ame_plan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_sum_jobs,
+    void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
-                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_peak, p->d_results};
+                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_peak, p->d_results};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->io_stream) cudaStreamDestroy(p->io_stream);
@@ -308,7 +311,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     // ---- job tables ---------------------------------------------------------------------------
     std::vector<TileJob> eq_jobs, split_jobs;
     std::vector<ChainJob> chain_jobs;
-    std::vector<SumJob> sum_jobs;
+    std::vector<WfJob> wf_jobs;
+    std::vector<MbChunk> mb_chunks;
     std::vector<KwJob> kw_jobs;
     std::vector<GainJob> gain_jobs;
     std::vector<int64_t> mb_delta(n_tracks, 0);
@@ -346,7 +350,13 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                             }
                         }
                         const double m = c.coef * over;
-                        e[r] = AttEntry{m, m / c.attack_frames, m / c.release_frames, 0.0};
+                        const double inc = m / c.attack_frames;
+                        // tau: smallest a >= 0 with fl(a + inc) >= m (fl(a + inc) is monotone in a)
+                        double tau = m - inc;
+                        if (!(tau > 0)) tau = 0.0;
+                        while (tau > 0 && tau + inc >= m) tau = std::nextafter(tau, -1.0);
+                        while (tau + inc < m) tau = std::nextafter(tau, 1e300);
+                        e[r] = AttEntry{m, inc, m / c.release_frames, tau};
                     }
                     c.table = idx;
                 } else {
@@ -361,19 +371,21 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
             if (mb) {
                 tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
+                MbChunk ck{cb, p->mb_offset[t] + c0, cn, p->n_seg_total, {0, 0, 0}, t, 0};
                 for (int b = 0; b < 3; ++b) {
                     const double thr = tp.comp[b].thresh_rms;
                     const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
-                    chain_jobs.push_back(ChainJob{p->mb_offset[t] + c0, cn, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
+                    ck.ck_begin[b] = p->n_group_total;
+                    chain_jobs.push_back(ChainJob{ck.mb_begin, cn, p->n_group_total, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
+                    p->n_group_total += (cn + 31) / 32;
                 }
+                p->n_seg_total += (cn + kSeg - 1) / kSeg;
+                mb_chunks.push_back(ck);
             }
             c0 += cn;
         }
         pad_jobs(eq_jobs, eq_first);
         pad_jobs(split_jobs, split_first);
-        if (mb)
-            for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
-                sum_jobs.push_back(SumJob{p->mb_offset[t] + b, tp.offset_frames + b, std::min<int64_t>(kGainTile, tp.n_frames - b)});
         for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
             kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
         for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
@@ -381,24 +393,28 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     }
     // longest chains first: the sequential compressor kernel is bounded by its slowest warp
     std::stable_sort(chain_jobs.begin(), chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
+    for (int c = 0; c < (int)chain_jobs.size(); ++c)
+        for (int64_t tb = 0; tb < chain_jobs[c].n; tb += kWfTile) wf_jobs.push_back(WfJob{c, 0, tb});
 
     p->n_eq_jobs = (int)eq_jobs.size();
     p->n_split_jobs = (int)split_jobs.size();
     p->n_chain_jobs = (int)chain_jobs.size();
-    p->n_sum_jobs = (int)sum_jobs.size();
+    p->n_wf_jobs = (int)wf_jobs.size();
+    p->n_mb_chunks = (int)mb_chunks.size();
     p->n_kw_jobs = (int)kw_jobs.size();
     p->n_gain_jobs = (int)gain_jobs.size();
-    p->ring_size = 128;
-    while (p->ring_size < p->max_look + 64) p->ring_size <<= 1;
 
     // ---- device state -------------------------------------------------------------------------
     if ((rc = upload(&p->d_tracks, p->tracks)) || (rc = upload(&p->d_tdev, p->tdev)) || (rc = upload(&p->d_mb_delta, mb_delta)) ||
         (rc = upload(&p->d_eq_jobs, eq_jobs)) || (rc = upload(&p->d_split_jobs, split_jobs)) ||
-        (rc = upload(&p->d_chain_jobs, chain_jobs)) || (rc = upload(&p->d_sum_jobs, sum_jobs)) ||
+        (rc = upload(&p->d_chain_jobs, chain_jobs)) || (rc = upload(&p->d_wf_jobs, wf_jobs)) || (rc = upload(&p->d_mb_chunks, mb_chunks)) ||
         (rc = upload(&p->d_kw_jobs, kw_jobs)) || (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_tables, tables)))
         return bail(rc);
     const size_t fb = (size_t)p->total_frames * 4;
     if ((rc = dmalloc(p, (void **)&p->d_pre, fb)) || (rc = dmalloc(p, (void **)&p->d_bands, (size_t)p->mb_frames * 4 * 3)) ||
+        (rc = dmalloc(p, (void **)&p->d_rms, (size_t)p->mb_frames * 2 * 3)) ||
+        (rc = dmalloc(p, (void **)&p->d_ckpt, (size_t)p->n_group_total * 8)) ||
+        (rc = dmalloc(p, (void **)&p->d_attf, (size_t)p->mb_frames * 8 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_energy, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
@@ -421,12 +437,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         if (cudaMemcpyToSymbol(c_hist_bounds, bounds, sizeof bounds) != cudaSuccess ||
             cudaMemcpyToSymbol(c_hist_energy, energies, sizeof energies) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError())));
-    }
-    {
-        const size_t smem = (size_t)kCompWarps * p->ring_size * 8;
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(k_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return bail(fail(AME_E_CUDA, "cannot reserve %zu bytes of shared memory", smem));
     }
     *out = p;
     return AME_OK;
@@ -517,16 +527,20 @@ int ame_stage_compress(ame_plan *p, int16_t *d_bands, int16_t *d_pre, void *stre
     cudaStream_t s = (cudaStream_t)stream;
     if (!p->n_chain_jobs) return AME_OK;
     if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-    const size_t smem = (size_t)kCompWarps * p->ring_size * 8;
-    t_begin(p, S_COMP, s);
-    k_compress<<<(p->n_chain_jobs + kCompWarps - 1) / kCompWarps, kCompWarps * 32, smem, s>>>(
-        p->d_chain_jobs, p->n_chain_jobs, d_bands, p->d_tables, p->mb_frames, p->ring_size);
+    t_begin(p, S_FLAG, s);
+    k_window_flag<<<p->n_wf_jobs, kWfThreads, 0, s>>>(p->d_wf_jobs, p->d_chain_jobs, d_bands, p->d_rms, p->mb_frames);
     LAUNCH_CHECK(p);
-    t_end(p, S_COMP, s);
-    t_begin(p, S_SUM, s);
-    k_band_sum<<<p->n_sum_jobs, 256, 0, s>>>(p->d_sum_jobs, d_bands, d_pre, p->mb_frames);
+    t_end(p, S_FLAG, s);
+    t_begin(p, S_CHAIN, s);
+    k_att_chain<<<(p->n_chain_jobs + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, s>>>(
+        p->d_chain_jobs, p->n_chain_jobs, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
     LAUNCH_CHECK(p);
-    t_end(p, S_SUM, s);
+    t_end(p, S_CHAIN, s);
+    t_begin(p, S_APPLY, s);
+    k_compress_apply<<<(unsigned)((p->n_seg_total + 3) / 4), 128, 0, s>>>(p->d_mb_chunks, p->n_mb_chunks, p->n_seg_total, d_bands,
+                                                                         p->d_rms, p->d_ckpt, p->d_attf, d_pre, p->mb_frames);
+    LAUNCH_CHECK(p);
+    t_end(p, S_APPLY, s);
     return AME_OK;
 }
 

@@ -30,6 +30,7 @@ struct TileJob {           // one lane pair of k_eq / k_band_split
 struct ChainJob {          // one warp of k_compress: one band of one chunk of a multiband track
     int64_t mb_begin;      // of the chunk, in the multiband-only packing (bands planes)
     int64_t n;             // frames
+    int64_t ck_begin;      // first slot of this chain in the per-group checkpoint array
     int32_t band;
     int32_t table;
     uint32_t thr_i;        // rms > thresh_rms  <=>  rms >= thr_i
@@ -40,9 +41,9 @@ struct KwJob { int32_t track; int32_t sb_begin; int32_t sb_end; int32_t pad; };
 
 struct GainJob { int64_t begin; int64_t end; int32_t track; int32_t pad; };
 
-struct SumJob { int64_t mb_begin; int64_t abs_begin; int64_t n; };   // both begins are multiples of 4
-
-struct AttEntry { double m, inc, dec, pad; };   // indexed by integer rms 0..32768
+// indexed by integer rms 0..32768.  tau = the smallest attenuation a with fl(a + inc) >= m, so that
+// (att + inc < m) <=> (att < tau) exactly and the branch predicates depend on the OLD attenuation only.
+struct AttEntry { double m, inc, dec, tau; };
 
 struct TrackDev {          // device-side per-track bookkeeping
     int64_t sb_offset;     // start of this track's 100 ms energies in the energy array
@@ -375,24 +376,290 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_compress: pydub compress_dynamic_range on one band of one chunk, ONE WARP per (chunk, band), in place
-// on the band plane.  Per group of 32 frames (lane = frame):
-//   B-stage (time-parallel): energy e = l^2 + r^2, warp inclusive scan -> exclusive prefix P(i) kept in a
-//     shared-memory ring; window sum S = P(i) - P(i - min(i, look)) (exact integers; pydub's
-//     rms_at(i) = audioop.rms of frames [max(i-look,0), i) = (unsigned)sqrt(S / n)).
-//     rms > thresh  <=>  rms >= thr_i  <=>  S >= thr_i^2 * n : an integer compare, so only flagged lanes
-//     take the square root (exact: S/n is never within 2^-41 of a perfect square unless it is one) and
-//     fetch (M, inc, dec) for their integer rms from the host-built table into shared memory.
-//   C-stage (sequential): walk the flagged frames in order (ballot + ffs):
-//       att = (att <= M) ? min(att + inc, M) : max(att - dec, 0)
-//     evaluated as  p = att > M ; s = att + inc ; att' = p ? att - dec : (s < M ? s : M)  with the
-//     comparisons done on the raw bit patterns (all operands are non-negative doubles, for which integer
-//     order == numeric order; att - dec >= M - M/release > 0 so the max() never binds): DADD + integer
-//     compare + select instead of DADD + two DSETP-based fmin/fmax (8 + ~12 cycles instead of ~40).
-//     Below threshold M = 0 => the attenuation is frozen (the reference's never-release quirk), so
-//     unflagged frames cost nothing.  Every lane then takes the attenuation in force at its own frame,
-//     gain = 10^(-att/20), audioop.mul = floor(clip(x * gain)).
+// Multiband compressor = pydub compress_dynamic_range per band (:306-308), split by what is sequential:
+//   k_window_flag   (time-parallel)  window rms of the previous look_frames frames; emits the integer rms
+//                                    for frames ABOVE threshold and 0 otherwise (2 B per band frame)
+//   k_att_chain     (sequential)     one warp per (chunk, band): walks ONLY the flagged frames and runs the
+//                                    attenuation recurrence; emits the attenuation entering each 32-frame
+//                                    group (8 B per group).  Below threshold the reference never releases
+//                                    (max_attenuation = 0 => dec = 0), so unflagged frames are no-ops.
+//   k_compress_apply (time-parallel) per 32-frame group: replay the recurrence inside the group from its
+//                                    entry value (bit-identical arithmetic), gain = 10^(-att/20),
+//                                    audioop.mul, and low.overlay(mid).overlay(high) (:309) into `pre`.
+// pydub: rms_at(i) = audioop.rms(frames [max(i-look,0), i)) = (unsigned)sqrt(S / n) with S the exact integer
+// sum of squares and n = 2 * frames.  rms > thresh  <=>  rms >= thr_i  <=>  S >= thr_i^2 * n (integers), so
+// only flagged frames take the square root (S/n is never within 2^-41 of a perfect square unless equal,
+// hence the double-precision expression of audioop truncates to the exact integer root).
 // ------------------------------------------------------------------------------------------------
+constexpr int kWfThreads = 256;
+constexpr int kWfTile = 2048;      // frames per CTA of k_window_flag (8 per thread)
+constexpr int kSeg = 256;          // frames per k_att_chain iteration / per k_compress_apply warp (8 groups)
+
+struct WfJob { int32_t chain; int32_t pad; int64_t tile_begin; };   // tile_begin relative to the chunk
+
+struct MbChunk {           // one chunk of a multiband track (k_compress_apply)
+    int64_t abs_begin;     // absolute frame index in the packed pre buffer
+    int64_t mb_begin;      // frame index in the multiband-only packing
+    int64_t n;             // frames
+    int64_t seg_prefix;    // kSeg-segments in all earlier chunks
+    int64_t ck_begin[3];   // first group slot of each band's chain in the checkpoint array
+    int32_t track;
+    int32_t pad;
+};
+
+__device__ __forceinline__ unsigned energy_of(uint32_t w) {          // l^2 + r^2 <= 2^31
+    const int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
+    return (unsigned)(l * l) + (unsigned)(r * r);
+}
+
+__device__ __forceinline__ void load8(const uint32_t *__restrict__ p, int64_t idx, int64_t lo, int64_t hi, uint32_t *w) {
+    // 8 consecutive frames p[idx .. idx+8) with frames outside [lo, hi) read as zero
+    if (idx >= lo && idx + 8 <= hi && ((reinterpret_cast<uintptr_t>(p + idx) & 15) == 0)) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p + idx));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p + idx) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = (idx + k >= lo && idx + k < hi) ? __ldg(p + idx + k) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kWfThreads)
+k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chains, const int16_t *__restrict__ bands,
+              uint16_t *__restrict__ rms, int64_t mb_frames) {
+    __shared__ long long s_scan[kWfThreads / 32];
+    __shared__ unsigned long long s_head[kWfThreads / 32];
+    const WfJob job = jobs[blockIdx.x];
+    const ChainJob cj = chains[job.chain];
+    const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)cj.band * mb_frames + cj.mb_begin;
+    uint16_t *rp = rms + (int64_t)cj.band * mb_frames + cj.mb_begin;
+    const int64_t n = cj.n, t0 = job.tile_begin;
+    const int look = cj.look;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t i0 = t0 + (int64_t)threadIdx.x * 8;
+    // window sum entering the tile: frames [t0 - look, t0)
+    unsigned long long head = 0;
+    for (int64_t j = t0 - look + threadIdx.x; j < t0; j += kWfThreads)
+        if (j >= 0) head += energy_of(__ldg(bp + j));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) head += __shfl_xor_sync(kFull, head, d);
+    if (lane == 0) s_head[wid] = head;
+    // D_j = e_j - e_{j-look}; S_i = head + sum_{t0 <= j < i} D_j
+    uint32_t w[8], wo[8];
+    load8(bp, i0, 0, n, w);
+    load8(bp, i0 - look, 0, n, wo);
+    long long pre[8];          // exclusive prefix of D inside the thread
+    long long run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        pre[k] = run;
+        run += (long long)energy_of(w[k]) - (long long)energy_of(wo[k]);
+    }
+    long long incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    long long base = incl - run;
+    unsigned long long h = 0;
+#pragma unroll
+    for (int q = 0; q < kWfThreads / 32; ++q) {
+        if (q < wid) base += s_scan[q];
+        h += s_head[q];
+    }
+    base += (long long)h;
+    const unsigned long long thr2 = (unsigned long long)cj.thr_i * cj.thr_i;
+    const bool never = cj.thr_i > 32768u;          // rms <= 32768 can never exceed it
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t i = i0 + k;
+        const long long s = base + pre[k];
+        const int64_t nfr = i < look ? i : look;
+        unsigned r = 0;
+        if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
+            r = __double2uint_rz(__dsqrt_rn(__ddiv_rn((double)s, (double)(2 * nfr))));
+        o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
+    }
+    if (i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(rp + i0) & 15) == 0)) {
+        *reinterpret_cast<uint4 *>(rp + i0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k < n) rp[i0 + k] = (uint16_t)(o[k >> 1] >> ((k & 1) * 16));
+    }
+}
+
+// att' = (att <= M) ? min(att + inc, M) : max(att - dec, 0), evaluated as
+//   att > M ? att - dec : (att < tau ? att + inc : M)
+// * max(., 0) never binds: att - dec > M - M/release_frames >= 0.
+// * tau is precomputed per table entry (host), so BOTH predicates are functions of the old attenuation and
+//   evaluate in parallel with the two DADDs; the loop-carried path is max(DADD, compare) + select, ~18 cycles
+//   on B200 against ~36 for DADD -> fmin (DSETP + FSEL) -> select (profiles/micro/att_chain_latency.cu).
+// * all operands are non-negative doubles, for which integer order of the bit patterns == numeric order.
+__device__ __forceinline__ double att_update(double att, double m, double inc, double dec, double tau) {
+    const long long ia = __double_as_longlong(att);
+    const bool above = ia > __double_as_longlong(m);
+    const bool rising = ia < __double_as_longlong(tau);
+    const double s = att + inc;
+    const double d = att - dec;
+    const double r = above ? d : m;
+    return (rising && !above) ? s : r;
+}
+
+constexpr int kChainWarps = 2;
+
+// k_att_chain: the strictly sequential part, one warp per (chunk, band).  Per 256-frame segment the lanes
+// compact the table entries of the flagged frames (lane = 8 consecutive frames) into shared memory in time
+// order; the recurrence then runs over that dense queue (operands at consecutive addresses, so the loads
+// pipeline ahead of the dependent DADD -> integer-compare -> select chain).  Outputs: the attenuation after
+// every flagged frame (att_f, sparse writes) and the attenuation entering every 32-frame group (ckpt).
+__global__ void __launch_bounds__(kChainWarps * 32)
+k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
+            const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
+    // per warp, double buffered: table entries of the flagged frames of one 256-frame segment, compacted in time
+    // order and padded to a multiple of 16 with no-op entries
+    __shared__ double2 s_mt[kChainWarps][2][kSeg + 16];   // (M, tau)
+    __shared__ double2 s_id[kChainWarps][2][kSeg + 16];   // (inc, dec)
+    __shared__ double s_att[kChainWarps][kSeg + 16];      // attenuation after each flagged frame
+    const int wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * kChainWarps + wib;
+    if (warp >= n_jobs) return;
+    const int lane = threadIdx.x & 31;
+    const ChainJob job = jobs[warp];
+    double *__restrict__ qa = s_att[wib];
+    const AttEntry *tbl = tables + (size_t)job.table * 32769;
+    const uint16_t *rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
+    double *af = att_f + (int64_t)job.band * mb_frames + job.mb_begin;
+    double *ck = ckpt + job.ck_begin;
+    const int64_t n = job.n;
+    const int64_t n_groups = (n + 31) >> 5;
+    const int64_t n_seg = (n + kSeg - 1) / kSeg;
+    const bool vec = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
+
+    auto load_seg = [&](int64_t seg, uint32_t *h) {     // this lane's 8 rms values as 4 words
+        const int64_t i = seg * kSeg + lane * 8;
+        h[0] = h[1] = h[2] = h[3] = 0;
+        if (seg >= n_seg) return;
+        if (vec && i + 8 <= n) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(rp + i));
+            h[0] = q.x; h[1] = q.y; h[2] = q.z; h[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i + k < n) h[k >> 1] |= (uint32_t)__ldg(rp + i + k) << ((k & 1) * 16);
+        }
+    };
+    struct SegInfo { unsigned m8; int off, total, before_grp; };
+    auto prep = [&](const uint32_t *h) -> SegInfo {     // compaction geometry of a segment
+        SegInfo si;
+        si.m8 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((h[k >> 1] >> ((k & 1) * 16)) & 0xffffu) si.m8 |= 1u << k;
+        const int cnt = __popc(si.m8);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        si.total = __shfl_sync(kFull, incl, 31);
+        si.off = incl - cnt;
+        // number of flagged frames before group g = exclusive count at lane 4g; lane g keeps it
+        si.before_grp = __shfl_sync(kFull, si.off, (lane & 7) * 4);
+        return si;
+    };
+    double2 e01[8], e23[8];                             // table entries of this lane's flagged frames, in flight
+    auto gather_issue = [&](const uint32_t *h) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned r = (h[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            if (r) {
+                e01[k] = __ldg(reinterpret_cast<const double2 *>(tbl + r));
+                e23[k] = __ldg(reinterpret_cast<const double2 *>(tbl + r) + 1);
+            }
+        }
+    };
+    auto gather_commit = [&](int buf, const SegInfo &si) {
+        double2 *qmt = s_mt[wib][buf], *qid = s_id[wib][buf];
+        int slot = si.off;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (si.m8 & (1u << k)) {
+                qmt[slot] = make_double2(e01[k].x, e23[k].y);
+                qid[slot] = make_double2(e01[k].y, e23[k].x);
+                ++slot;
+            }
+        // no-op entries: M < 0 => "above", dec = 0 => att unchanged
+        if (lane < 16) { qmt[si.total + lane] = make_double2(-1.0, 0.0); qid[si.total + lane] = make_double2(0.0, 0.0); }
+    };
+
+    double att = 0.0;
+    uint32_t cur[4], nx1[4], nx2[4];                   // rms words are fetched two segments ahead
+    load_seg(0, cur);
+    load_seg(1, nx1);
+    SegInfo sc = prep(cur);
+    if (sc.total) { gather_issue(cur); gather_commit(0, sc); }
+    __syncwarp();
+    for (int64_t seg = 0; seg < n_seg; ++seg) {
+        const int buf = (int)(seg & 1);
+        load_seg(seg + 2, nx2);
+        const SegInfo sn = prep(nx1);
+        if (sn.total) gather_issue(nx1);               // next segment's table entries fly during this chain
+        const double att_in = att;
+        if (sc.total) {
+            // The recurrence proper: 16 steps per iteration from two ping-pong register blocks, so the shared
+            // memory loads of the next 8 steps are in flight while the current 8 run.  Measured on B200: 25
+            // cycles per dependent step in this shape against 55 when every step reads its operands from shared
+            // memory, and 75 with regime speculation on real signals whose regime flips almost every frame
+            // (profiles/micro/att_chain_latency3.cu).
+            const double2 *__restrict__ qmt = s_mt[wib][buf];
+            const double2 *__restrict__ qid = s_id[wib][buf];
+            double2 A0[8], A1[8], B0[8], B1[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { A0[k] = qmt[k]; A1[k] = qid[k]; }
+            for (int j0 = 0; j0 < sc.total; j0 += 16) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { B0[k] = qmt[j0 + 8 + k]; B1[k] = qid[j0 + 8 + k]; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    att = att_update(att, A0[k].x, A1[k].x, A1[k].y, A0[k].y);
+                    qa[j0 + k] = att;
+                }
+                if (j0 + 16 < sc.total) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { A0[k] = qmt[j0 + 16 + k]; A1[k] = qid[j0 + 16 + k]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    att = att_update(att, B0[k].x, B1[k].x, B1[k].y, B0[k].y);
+                    qa[j0 + 8 + k] = att;
+                }
+            }
+        }
+        if (sn.total) gather_commit(buf ^ 1, sn);
+        __syncwarp();
+        double ge = att_in;                            // lane g (< 8): attenuation entering group g
+        if (sc.total) {
+            // = value after the flagged frames that precede the group in this segment
+            if (sc.before_grp) ge = qa[sc.before_grp - 1];
+            int slot = sc.off;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (sc.m8 & (1u << k)) af[seg * kSeg + lane * 8 + k] = qa[slot++];
+        }
+        if (lane < 8 && seg * 8 + lane < n_groups) ck[seg * 8 + lane] = ge;
+        __syncwarp();                                  // qa is rewritten by the next segment's chain
+        sc = sn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cur[k] = nx1[k]; nx1[k] = nx2[k]; }
+    }
+}
+
 __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
     double v = __dmul_rn((double)x, f);
     if (v > 32767.0) v = 32767.0;
@@ -400,166 +667,62 @@ __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fboun
     return __double2int_rd(v);
 }
 
-__device__ __forceinline__ double att_update(double att, double m, double inc, double dec) {
-    const long long ia = __double_as_longlong(att), im = __double_as_longlong(m);
-    const double s = att + inc;
-    const double d = att - dec;
-    const long long is = __double_as_longlong(s);
-    const double r = (ia > im) ? d : m;           // ready early: does not depend on s
-    return (ia <= im && is < im) ? s : r;
-}
-
-constexpr int kCompWarps = 4;      // warps (chains) per CTA
-constexpr int kCompBatch = 4;      // groups of 32 frames per pipeline step
-
-struct CompShared {                // per warp
-    double2 e01[kCompBatch][32];   // (M, inc) of each lane's frame
-    double e2[kCompBatch][32];     // dec
-    double att[kCompBatch][32];    // attenuation after each flagged frame
-};
-
-__global__ void __launch_bounds__(kCompWarps * 32)
-k_compress(const ChainJob *__restrict__ jobs, int n_jobs, int16_t *__restrict__ bands,
-           const AttEntry *__restrict__ tables, int64_t mb_frames, int ring_size) {
-    extern __shared__ unsigned long long s_dyn[];            // [kCompWarps][ring_size] exclusive prefixes
-    __shared__ CompShared s_comp[kCompWarps];
-    const int wib = threadIdx.x >> 5;
-    const int warp = blockIdx.x * kCompWarps + wib;
-    if (warp >= n_jobs) return;
+// k_compress_apply: one warp per 256-frame segment, all three bands.  The attenuation in force at a frame is
+// the value k_att_chain stored for the last flagged frame at or before it inside its 32-frame group, or the
+// group's entry value; gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)), skipped
+// when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
+__global__ void __launch_bounds__(128)
+k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg_total,
+                 const int16_t *__restrict__ bands, const uint16_t *__restrict__ rms,
+                 const double *__restrict__ ckpt, const double *__restrict__ att_f, int16_t *__restrict__ pre,
+                 int64_t mb_frames) {
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= n_seg_total) return;
     const int lane = threadIdx.x & 31;
-    const ChainJob job = jobs[warp];
-    unsigned long long *ring = s_dyn + (size_t)wib * ring_size;
-    CompShared &sh = s_comp[wib];
-    const int rmask = ring_size - 1;
-    const AttEntry *tbl = tables + (size_t)job.table * 32769;
-    uint32_t *bp = reinterpret_cast<uint32_t *>(bands) + (int64_t)job.band * mb_frames + job.mb_begin;
-    const int64_t n = job.n;
-    const int64_t n_groups = (n + 31) >> 5;
-    const int look = job.look;
-    const unsigned long long thr2 = (unsigned long long)job.thr_i * job.thr_i;   // thr_i <= 2^31 is capped on the host
-    const bool never = job.thr_i > 32768u;   // rms <= 32768: cannot trigger (also keeps thr2 * n inside 64 bits)
-
-    unsigned long long carry = 0;  // sum of energies of all frames before the current group
-
-    // B-stage of one group; returns the ballot of flagged lanes, leaves their table entries in shared memory
-    auto b_stage = [&](int slot, int64_t grp, uint32_t w) -> unsigned {
-        const int64_t i = grp * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t wv = valid ? w : 0u;
-        const int l = (int16_t)(wv & 0xffffu), r = (int16_t)(wv >> 16);
-        const unsigned e = (unsigned)(l * l) + (unsigned)(r * r);          // <= 2^31
-        unsigned long long incl = e;
+    int lo = 0, hi = n_chunks - 1;                 // last chunk with seg_prefix <= seg
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (chunks[mid].seg_prefix <= seg) lo = mid; else hi = mid - 1;
+    }
+    const MbChunk ck = chunks[lo];
+    const int64_t lseg = seg - ck.seg_prefix;
+    const int64_t f0 = lseg * kSeg;
+    const int64_t n = ck.n;
+    int accl[8], accr[8];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long v = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const unsigned long long pex = carry + incl - e;       // sum of e over frames < i
-        carry += __shfl_sync(kFull, incl, 31);
-        ring[(int)(i & rmask)] = pex;
-        __syncwarp();
-        const int64_t nfr = i < look ? i : look;
-        const unsigned long long s = pex - ring[(int)((i - nfr) & rmask)];
-        const bool flag = valid && !never && nfr > 0 && s >= thr2 * (unsigned long long)(2 * nfr);
-        const unsigned ballot = __ballot_sync(kFull, flag);
-        if (flag) {
-            const unsigned rms = __double2uint_rz(__dsqrt_rn(__ddiv_rn((double)s, (double)(2 * nfr))));
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(tbl + rms));
-            const double2 b = __ldg(reinterpret_cast<const double2 *>(tbl + rms) + 1);
-            sh.e01[slot][lane] = a;
-            sh.e2[slot][lane] = b.x;
-        }
-        return ballot;
-    };
-
-    double att = 0.0;              // warp-uniform attenuation state (dB)
-    double c_att = 0.0, c_fac = 1.0;   // per-lane cache of the last gain computed
-
-    auto c_stage = [&](int slot, int64_t grp, uint32_t w, unsigned ballot) {
-        const double att_in = att;
-        if (ballot) {
-            __syncwarp();          // entries written by the flagged lanes are visible
-            if (ballot == kFull) { // dense: fixed trip count, the broadcasts schedule ahead of the chain
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) {
-                    const double2 a = sh.e01[slot][k];
-                    att = att_update(att, a.x, a.y, sh.e2[slot][k]);
-                    sh.att[slot][k] = att;
-                }
-            } else {
-                unsigned todo = ballot;
-                int k = __ffs(todo) - 1;
-                double2 a = sh.e01[slot][k];
-                double dec = sh.e2[slot][k];
-                while (true) {
-                    todo &= todo - 1;
-                    const int kn = todo ? __ffs(todo) - 1 : k;     // prefetch the next entry
-                    const double2 an = sh.e01[slot][kn];
-                    const double decn = sh.e2[slot][kn];
-                    att = att_update(att, a.x, a.y, dec);
-                    sh.att[slot][k] = att;
-                    if (!todo) break;
-                    k = kn; a = an; dec = decn;
+    for (int b = 0; b < 3; ++b) {
+        const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)b * mb_frames + ck.mb_begin;
+        const uint16_t *rp = rms + (int64_t)b * mb_frames + ck.mb_begin;
+        const double *ap = att_f + (int64_t)b * mb_frames + ck.mb_begin;
+        const double *cp = ckpt + ck.ck_begin[b] + lseg * 8;
+        double c_att = 0.0, c_fac = 1.0;           // per-lane cache of the last gain computed
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int64_t i = f0 + g * 32 + lane;
+            int l = 0, r = 0;
+            if (f0 + g * 32 < n) {                 // warp-uniform
+                const bool valid = i < n;
+                const unsigned rv = valid ? (unsigned)__ldg(rp + i) : 0u;
+                const uint32_t w = valid ? __ldg(bp + i) : 0u;
+                const unsigned flags = __ballot_sync(kFull, rv != 0);
+                const unsigned below = flags & (0xffffffffu >> (31 - lane));
+                const double mine = below ? __ldg(ap + (i - lane) + (31 - __clz(below))) : __ldg(cp + g);
+                l = (int16_t)(w & 0xffffu); r = (int16_t)(w >> 16);
+                if (mine != 0.0) {
+                    if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
+                    l = mul_floor(l, c_fac);
+                    r = mul_floor(r, c_fac);
                 }
             }
-            __syncwarp();
+            accl[g] = b ? sat16(accl[g] + l) : l;
+            accr[g] = b ? sat16(accr[g] + r) : r;
         }
-        // attenuation in force at this lane's frame = after the last flagged frame <= lane
-        const unsigned below = ballot & (0xffffffffu >> (31 - lane));
-        const double mine = below ? sh.att[slot][31 - __clz(below)] : att_in;
-        const int64_t i = grp * 32 + lane;
-        if (mine != 0.0 && i < n) {
-            if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
-            const int l = mul_floor((int16_t)(w & 0xffffu), c_fac);
-            const int r = mul_floor((int16_t)(w >> 16), c_fac);
-            bp[i] = pack16(l, r);
-        }
-    };
-
-    // band words are fetched one batch (kCompBatch groups) ahead; per batch: B-stages, then the sequential C-stages
-    uint32_t wq[kCompBatch], wc[kCompBatch];
-    unsigned bc[kCompBatch];
-    auto load_batch = [&](int64_t g0) {
-#pragma unroll
-        for (int j = 0; j < kCompBatch; ++j) {
-            const int64_t i = (g0 + j) * 32 + lane;
-            wq[j] = (i < n) ? bp[i] : 0u;
-        }
-    };
-    load_batch(0);
-#pragma unroll
-    for (int j = 0; j < kCompBatch; ++j) wc[j] = wq[j];
-    for (int64_t g0 = 0; g0 < n_groups; g0 += kCompBatch) {
-        load_batch(g0 + kCompBatch);
-#pragma unroll
-        for (int j = 0; j < kCompBatch; ++j) bc[j] = b_stage(j, g0 + j, wc[j]);
-#pragma unroll
-        for (int j = 0; j < kCompBatch; ++j) c_stage(j, g0 + j, wc[j], bc[j]);
-#pragma unroll
-        for (int j = 0; j < kCompBatch; ++j) wc[j] = wq[j];
     }
-}
-
-// k_band_sum: low.overlay(mid).overlay(high) (:309) = audioop.add twice = saturating int16 adds
-__global__ void __launch_bounds__(256)
-k_band_sum(const SumJob *__restrict__ jobs, const int16_t *__restrict__ bands, int16_t *__restrict__ pre, int64_t mb_frames) {
-    const SumJob job = jobs[blockIdx.x];
-    const uint4 *p0 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + job.mb_begin);
-    const uint4 *p1 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + mb_frames + job.mb_begin);
-    const uint4 *p2 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(bands) + 2 * mb_frames + job.mb_begin);
-    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(pre) + job.abs_begin);
-    const int64_t nv = (job.n + 3) >> 2;
-    for (int64_t v = threadIdx.x; v < nv; v += blockDim.x) {
-        const uint4 a = __ldg(p0 + v), b = __ldg(p1 + v), c = __ldg(p2 + v);
-        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w}, wc[4] = {c.x, c.y, c.z, c.w};
-        uint32_t o[4];
+    uint32_t *out = reinterpret_cast<uint32_t *>(pre) + ck.abs_begin;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int l = sat16(sat16((int16_t)(wa[k] & 0xffffu) + (int16_t)(wb[k] & 0xffffu)) + (int16_t)(wc[k] & 0xffffu));
-            const int r = sat16(sat16((int16_t)(wa[k] >> 16) + (int16_t)(wb[k] >> 16)) + (int16_t)(wc[k] >> 16));
-            o[k] = pack16(l, r);
-        }
-        dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int g = 0; g < 8; ++g) {
+        const int64_t i = f0 + g * 32 + lane;
+        if (i < n) out[i] = pack16(accl[g], accr[g]);
     }
 }
 

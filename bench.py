@@ -30,7 +30,8 @@ METRIC = "audio-sec mastered/sec (x realtime)"
 UNIT = "x realtime"
 B_ALG_CHAIN = 16       # bytes per stereo frame, whole chain with normalisation
 KERNEL_ALG_BYTES = {   # per-kernel algorithmic bytes per frame it processes
-    "k_eq": 8, "k_band_split": 16, "k_compress": 24, "k_band_sum": 16, "k_kweight_energy": 4, "k_apply_gain": 8}
+    "k_eq": 8, "k_band_split": 16, "k_window_flag": 18, "k_att_chain": 6, "k_compress_apply": 22,
+    "k_kweight_energy": 4, "k_apply_gain": 8}
 
 
 def parse():

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define AME_ABI_VERSION 1
-#define AME_N_KERNELS 9    /* kernels of the path, in launch order (ame_kernel_name) */
+#define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
     AME_OK = 0,
@@ -167,7 +167,7 @@ int ame_normalize_device(ame_plan *plan, const int64_t *d_hist, int16_t *d_out,
 int ame_stage_eq(ame_plan *plan, const int16_t *d_in, int16_t *d_pre, void *stream);
 /* crossover + int16 truncation of the three bands (:300-305); d_bands = 3 packed buffers back to back */
 int ame_stage_band_split(ame_plan *plan, const int16_t *d_pre, int16_t *d_bands, void *stream);
-/* pydub compress_dynamic_range on each band (in place on d_bands) + overlay into d_pre (:306-309) */
+/* pydub compress_dynamic_range on each band + overlay into d_pre (:306-309); d_bands is not modified */
 int ame_stage_compress(ame_plan *plan, int16_t *d_bands, int16_t *d_pre, void *stream);
 /* K-weighting + 100 ms energies + 400 ms block histogram (ebur128) */
 int ame_stage_loudness_hist(ame_plan *plan, const int16_t *d_pre, int64_t *d_hist, void *stream);
