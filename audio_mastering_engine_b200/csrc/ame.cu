@@ -152,7 +152,7 @@ int64_t pick_tile(const std::vector<std::vector<int64_t>> &chunks_per_track, int
         for (const auto &cs : chunks_per_track) {
             int64_t j = 0;
             for (int64_t n : cs) j += (n + T - 1) / T;
-            jobs += align_up(j, 16);
+            jobs += j;
         }
         return jobs;
     };
@@ -298,13 +298,13 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
-    p->eq_slots = n_sm * std::max(occ_eq, 1) * 64;
-    p->split_slots = n_sm * std::max(occ_split, 1) * 64;
+    p->eq_slots = n_sm * std::max(occ_eq, 1) * 128;      // one thread per tile
+    p->split_slots = n_sm * std::max(occ_split, 1) * 128;
     constexpr int64_t kMinTile = 512;
     p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)pick_tile(chunks_all, p->eq_slots, kMinTile);
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8)
                                             : (int)pick_tile(chunks_mb, p->split_slots, kMinTile);
-    const int64_t kw_slots = (int64_t)n_sm * 16 * 64;
+    const int64_t kw_slots = (int64_t)n_sm * 16 * 128;
     if (o.kw_tile_subblocks > 0) p->kw_tile_sb = o.kw_tile_subblocks;
     else p->kw_tile_sb = (int)std::max<int64_t>(1, (p->n_sb_total + kw_slots - 1) / kw_slots);
 
@@ -364,7 +364,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                 }
             }
         }
-        const size_t eq_first = eq_jobs.size(), split_first = split_jobs.size();
         int64_t c0 = 0;
         for (int64_t cn : chunks_all[t]) {
             const int64_t cb = tp.offset_frames + c0, ce = cb + cn;
@@ -384,8 +383,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             }
             c0 += cn;
         }
-        pad_jobs(eq_jobs, eq_first);
-        pad_jobs(split_jobs, split_first);
         for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
             kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
         for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
@@ -497,7 +494,7 @@ int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream)
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (p->n_eq_jobs) {
-        const int threads = 128, blocks = (p->n_eq_jobs * 2 + threads - 1) / threads;
+        const int threads = 128, blocks = (p->n_eq_jobs + threads - 1) / threads;
         t_begin(p, S_EQ, s);
         k_eq<<<blocks, threads, 0, s>>>(p->d_eq_jobs, p->n_eq_jobs, p->d_tracks, p->d_luts, d_in, d_pre);
         LAUNCH_CHECK(p);
@@ -512,7 +509,7 @@ int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, vo
     cudaStream_t s = (cudaStream_t)stream;
     if (p->n_split_jobs) {
         if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-        const int threads = 128, blocks = (p->n_split_jobs * 2 + threads - 1) / threads;
+        const int threads = 128, blocks = (p->n_split_jobs + threads - 1) / threads;
         t_begin(p, S_SPLIT, s);
         k_band_split<<<blocks, threads, 0, s>>>(p->d_split_jobs, p->n_split_jobs, p->d_tracks, p->d_mb_delta, d_pre, d_bands, p->mb_frames);
         LAUNCH_CHECK(p);
@@ -549,9 +546,8 @@ int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, 
     CU(cudaSetDevice(p->device));
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(p->d_peak, 0, (size_t)p->n_tracks * 4, s));
-    CU(cudaMemsetAsync(p->d_energy, 0, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8, s));
     if (p->n_kw_jobs) {
-        const int threads = 128, blocks = (p->n_kw_jobs * 2 + threads - 1) / threads;
+        const int threads = 128, blocks = (p->n_kw_jobs + threads - 1) / threads;
         t_begin(p, S_KW, s);
         k_kweight_energy<<<blocks, threads, 0, s>>>(p->d_kw_jobs, p->n_kw_jobs, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
         LAUNCH_CHECK(p);

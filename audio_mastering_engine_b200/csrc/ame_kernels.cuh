@@ -116,28 +116,21 @@ __device__ __forceinline__ double peak_step(const PeakCoef &c, double *z, double
     return bw_step1<-1>(c.a1[3], c.a2[3], z[6], z[7], t);
 }
 
-// warp-uniform group schedule shared by the lane-pair kernels
-struct GroupRange {
-    int64_t g0;      // first (4-aligned) frame of group 0
-    int n;           // groups of this pair
-    int n_max;       // warp maximum
-};
-__device__ __forceinline__ GroupRange group_range(int64_t f_lo, int64_t f_hi) {
-    GroupRange r;
-    r.g0 = f_lo & ~(int64_t)3;
-    r.n = f_hi > r.g0 ? (int)((f_hi - r.g0 + 3) >> 2) : 0;
-    r.n_max = __reduce_max_sync(kFull, r.n);
-    return r;
+// exact int16 -> x / 32768 as double in ONE add: bits of 2^37 + (x + 2^31) * 2^-15, minus 2^37 + 2^16
+__device__ __forceinline__ double i16_to_unit(int x) {
+    return __hiloint2double(0x42400000, (int)(0x80000000u ^ (unsigned)x)) - 137439019008.0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_eq: int16 in -> [warmth -> int16] -> float32 -> 4-stage EQ in FP64 -> float32 -> [width] -> int16
-// One lane per channel, lanes (2j, 2j+1) = (L, R) of job j.  MASK = active EQ stages, WARM = warmth on.
+// ONE THREAD per tile, both channels: the L and R cascades are two independent dependency chains in one
+// instruction stream (the kernel is bound by FP64 latency, not by registers), and the cross-channel
+// stages (warmth, width, packing) need no shuffles.  MASK = active EQ stages, WARM = warmth on.
 // ------------------------------------------------------------------------------------------------
 template <int MASK, bool WARM>
 __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
                                         const double *__restrict__ luts, const int16_t *__restrict__ in,
-                                        int16_t *__restrict__ pre, int ch) {
+                                        int16_t *__restrict__ pre) {
     const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
     const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
@@ -159,135 +152,120 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         s3_b0 = tp->eq[3].s[0].b0; s3_a1 = tp->eq[3].s[0].a1; s3_a2 = tp->eq[3].s[0].a2;
         g3 = tp->eq[3].g; gm3 = tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
     }
-    double z[20];
+    double zl[20], zr[20];
 #pragma unroll
-    for (int i = 0; i < 20; ++i) z[i] = 0.0;
+    for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
 
     const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
     int64_t f_lo = job.tile_begin - warm;
     if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
     const int64_t f_hi = job.tile_end;
-    const GroupRange gr = group_range(f_lo, f_hi);
+    if (f_hi <= f_lo) return;
+    const int64_t g0f = f_lo & ~(int64_t)3;               // first 4-aligned group
+    const int n_it = (int)((f_hi - g0f + 3) >> 2);
 
-    // one frame: returns this lane's int16 sample.  lutL / lutM = table values of the L sample and of this
-    // lane's own sample (fetched one group ahead).  Uses only full-mask shuffles.
-    auto frame = [&](uint32_t w, double lutL, double lutM) -> int {
-        int xm = ch ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xffffu);
+    auto cascade = [&](double v, double *z) -> float {     // one channel through the 4 EQ stages
+        if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
+            const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
+            v = boost0 ? v + (f - v) * gm0 : v * g0 + (f - v * g0);
+        }
+        if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
+        if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
+        if (MASK & 8) {   // apply_shelf_filter 8 kHz high
+            const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
+            v = boost3 ? v + (f - v) * gm3 : v * g3 + (f - v * g3);
+        }
+        return __double2float_rn(v);                       // samples[:, i] = ... into the float32 array (:274)
+    };
+
+    // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
+    auto frame = [&](uint32_t w, double lutL, double lutR) -> uint32_t {
+        int xl = (int)(int16_t)(w & 0xffffu), xr = (int)(int16_t)(w >> 16);
         if (WARM) {
             // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh, widened
-            // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels.
-            const double L = lutL;
-            double mine = lutM;
-            // 120 Hz low: y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y-x)*(g-1)
-            double t0 = __dmul_rn(wl_b0, mine);
-            double y0L = __dmul_rn(wl_b0, L);
-            double zz = __dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0L));
-            double y = ch ? __dadd_rn(zz, t0) : t0;
-            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0L, L), wl_gm1));
-            mine = __dadd_rn(mine, __dmul_rn(__dsub_rn(y, mine), wl_gm1));
-            // 12 kHz high, same structure on the blended values
-            t0 = __dmul_rn(wh_b0, mine);
-            y0L = __dmul_rn(wh_b0, L1);
-            zz = __dsub_rn(__dmul_rn(wh_b1, L1), __dmul_rn(wh_a1, y0L));
-            y = ch ? __dadd_rn(zz, t0) : t0;
-            mine = __dadd_rn(mine, __dmul_rn(__dsub_rn(y, mine), wh_gm1));
-            xm = to_pcm_f64(mine);               // float_array_to_audio_segment (:254-257)
+            // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels:
+            //   y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y - x)*(g - 1)       (no FMA contraction)
+            double L = lutL, R = lutR;
+            double y0 = __dmul_rn(wl_b0, L);
+            double y1 = __dadd_rn(__dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0)), __dmul_rn(wl_b0, R));
+            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), wl_gm1));
+            const double R1 = __dadd_rn(R, __dmul_rn(__dsub_rn(y1, R), wl_gm1));
+            y0 = __dmul_rn(wh_b0, L1);
+            y1 = __dadd_rn(__dsub_rn(__dmul_rn(wh_b1, L1), __dmul_rn(wh_a1, y0)), __dmul_rn(wh_b0, R1));
+            L = __dadd_rn(L1, __dmul_rn(__dsub_rn(y0, L1), wh_gm1));
+            R = __dadd_rn(R1, __dmul_rn(__dsub_rn(y1, R1), wh_gm1));
+            xl = to_pcm_f64(L);                            // float_array_to_audio_segment (:254-257)
+            xr = to_pcm_f64(R);
         }
         // audio_segment_to_float_array (:250-253): x / 32768 is exact in float32 and in float64
-        float yf;
+        float yl, yr;
         if (MASK != 0) {
-            double v = i16_to_f64(xm) * (1.0 / 32768.0);
-            if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
-                const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
-                v = boost0 ? v + (f - v) * gm0 : v * g0 + (f - v * g0);
-            }
-            if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
-            if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
-            if (MASK & 8) {   // apply_shelf_filter 8 kHz high
-                const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
-                v = boost3 ? v + (f - v) * gm3 : v * g3 + (f - v * g3);
-            }
-            yf = __double2float_rn(v);            // samples[:, i] = ... into the float32 array (:274)
+            yl = cascade(i16_to_unit(xl), zl);
+            yr = cascade(i16_to_unit(xr), zr);
         } else {
-            yf = __fmul_rn((float)xm, 1.0f / 32768.0f);
+            yl = __fmul_rn((float)xl, 1.0f / 32768.0f);
+            yr = __fmul_rn((float)xr, 1.0f / 32768.0f);
         }
         if (widen) {          // apply_stereo_width (:267-271), float32 arithmetic
-            const float other = __shfl_xor_sync(kFull, yf, 1);
-            const float l = ch ? other : yf, r = ch ? yf : other;
-            const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
-            const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), wfac);
-            yf = ch ? __fsub_rn(mid, side) : __fadd_rn(mid, side);
+            const float mid = __fmul_rn(__fadd_rn(yl, yr), 0.5f);
+            const float side = __fmul_rn(__fmul_rn(__fsub_rn(yl, yr), 0.5f), wfac);
+            yl = __fadd_rn(mid, side);
+            yr = __fsub_rn(mid, side);
         }
-        return to_pcm_f32(yf);                    // clip inside to_pcm == np.clip of (:270) then (:255)
+        return pack16(to_pcm_f32(yl), to_pcm_f32(yr));     // clip inside to_pcm == np.clip of (:270) then (:255)
     };
 
-    const uint4 *src = reinterpret_cast<const uint4 *>(in) + (gr.g0 >> 2);
-    uint4 *dst = reinterpret_cast<uint4 *>(pre) + (gr.g0 >> 2);
+    const uint4 *src = reinterpret_cast<const uint4 *>(in) + (g0f >> 2);
+    uint4 *dst = reinterpret_cast<uint4 *>(pre) + (g0f >> 2);
     // software pipeline: input words two groups ahead, tanh-table values one group ahead
-    auto mask_head = [&](uint4 q, int it) {   // frames before the chunk start must not disturb the zero state
-        const int64_t g = gr.g0 + 4 * (int64_t)it;
-        if (g + 0 < job.chunk_begin) q.x = 0;
-        if (g + 1 < job.chunk_begin) q.y = 0;
-        if (g + 2 < job.chunk_begin) q.z = 0;
-        return q;
-    };
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-    if (gr.n > 0) cur = mask_head(ldg16(src), 0);
-    if (gr.n > 1) nxt = ldg16(src + 1);
-    double lutL[4] = {0, 0, 0, 0}, lutM[4] = {0, 0, 0, 0};
-    auto fetch_lut = [&](const uint4 &q, double *l, double *m) {
+    uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
+    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // frames before the chunk start keep the zero state
+    if (g0f + 1 < job.chunk_begin) cur.y = 0;
+    if (g0f + 2 < job.chunk_begin) cur.z = 0;
+    if (n_it > 1) nxt = ldg16(src + 1);
+    double lutL[4] = {0, 0, 0, 0}, lutR[4] = {0, 0, 0, 0};
+    auto fetch_lut = [&](const uint4 &q, double *l, double *r) {
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
-            l[k] = __ldg(lut + xl);
-            m[k] = __ldg(lut + (ch ? xr : xl));
+            l[k] = __ldg(lut + (int)(int16_t)(w[k] & 0xffffu));
+            r[k] = __ldg(lut + (int)(int16_t)(w[k] >> 16));
         }
     };
-    if (WARM) fetch_lut(cur, lutL, lutM);
-    for (int it = 0; it < gr.n_max; ++it) {
+    if (WARM) fetch_lut(cur, lutL, lutR);
+    for (int it = 0; it < n_it; ++it) {
         uint4 nn = nxt;
-        if (it + 2 < gr.n) nn = ldg16(src + it + 2);
-        double nL[4] = {0, 0, 0, 0}, nM[4] = {0, 0, 0, 0};
-        if (WARM) fetch_lut(nxt, nL, nM);
-        const int64_t g = gr.g0 + 4 * (int64_t)it;
+        if (it + 2 < n_it) nn = ldg16(src + it + 2);
+        double nL[4] = {0, 0, 0, 0}, nR[4] = {0, 0, 0, 0};
+        if (WARM) fetch_lut(nxt, nL, nR);
+        const int64_t g = g0f + 4 * (int64_t)it;
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int mine = frame(w[k], lutL[k], lutM[k]);
-            const int other = __shfl_xor_sync(kFull, mine, 1);
-            o[k] = ch ? pack16(other, mine) : pack16(mine, other);
-        }
-        if (ch == 0 && it < gr.n) {
-            if (g >= job.tile_begin && g + 4 <= f_hi) {
-                dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
-            } else {
+        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k]);
+        if (g >= job.tile_begin && g + 4 <= f_hi) {
+            dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it)[k] = o[k];
-            }
+            for (int k = 0; k < 4; ++k)
+                if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it)[k] = o[k];
         }
         cur = nxt; nxt = nn;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutM[k] = nM[k]; }
+        for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutR[k] = nR[k]; }
     }
 }
 
-// The host pads every track's job list to a multiple of 16 pairs (empty jobs), so a warp never mixes tracks:
-// variant and flags are warp-uniform and the full-mask shuffles inside eq_tile are always converged.
 __global__ void __launch_bounds__(128, 2)
 k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
      const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (((tid & ~31) >> 1) >= n_jobs) return;     // whole warps only (n_jobs is a multiple of 16)
-    const int pair = tid >> 1;
-    const int ch = tid & 1;
-    const TileJob job = jobs[pair];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const TileJob job = jobs[j];
     const ame_track_params *tp = tracks + job.track;
     switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth
-#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre, ch); break; \
-                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre, ch); break;
+#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre); break; \
+                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre); break;
         AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
         AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
         AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
@@ -297,79 +275,68 @@ k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__res
 
 // ------------------------------------------------------------------------------------------------
 // k_band_split: int16 pre -> Butterworth-4 LP 250 / HP 4k in FP64, mid = x - low - high, each band
-// truncated to int16 (apply_multiband_compressor :300-305).  Same lane-pair / warm-up scheme.
-// bands = 3 planes of mb_frames frames each.
+// truncated to int16 (apply_multiband_compressor :300-305).  One thread per tile, both channels, same
+// warm-up scheme.  bands = 3 planes of mb_frames frames each.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
              const int64_t *__restrict__ mb_delta,   // per track: mb_offset - offset_frames
              const int16_t *__restrict__ pre, int16_t *__restrict__ bands, int64_t mb_frames) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (((tid & ~31) >> 1) >= n_jobs) return;
-    const int pair = tid >> 1;
-    const int ch = tid & 1;
-    const TileJob job = jobs[pair];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const TileJob job = jobs[j];
     const ame_track_params *tp = tracks + job.track;
     const double lb0 = tp->xlp[0].b0, la10 = tp->xlp[0].a1, la20 = tp->xlp[0].a2, la11 = tp->xlp[1].a1, la21 = tp->xlp[1].a2;
     const double hb0 = tp->xhp[0].b0, ha10 = tp->xhp[0].a1, ha20 = tp->xhp[0].a2, ha11 = tp->xhp[1].a1, ha21 = tp->xhp[1].a2;
     const int64_t delta = mb_delta[job.track];
-    double z[8];
+    double zl[8], zr[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+    for (int i = 0; i < 8; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
     int64_t f_lo = job.tile_begin - (int64_t)tp->warm_xover;
     if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
     const int64_t f_hi = job.tile_end;
-    const GroupRange gr = group_range(f_lo, f_hi);
+    if (f_hi <= f_lo) return;
+    const int64_t g0f = f_lo & ~(int64_t)3;
+    const int n_it = (int)((f_hi - g0f + 3) >> 2);
     uint32_t *b0 = reinterpret_cast<uint32_t *>(bands) + delta;
     uint32_t *b1 = b0 + mb_frames;
     uint32_t *b2 = b1 + mb_frames;
 
-    const uint4 *src = reinterpret_cast<const uint4 *>(pre) + (gr.g0 >> 2);
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-    if (gr.n > 0) {
-        cur = ldg16(src);
-        if (gr.g0 + 0 < job.chunk_begin) cur.x = 0;   // keep the zero state until the chunk starts
-        if (gr.g0 + 1 < job.chunk_begin) cur.y = 0;
-        if (gr.g0 + 2 < job.chunk_begin) cur.z = 0;
-    }
-    if (gr.n > 1) nxt = ldg16(src + 1);
-    for (int it = 0; it < gr.n_max; ++it) {
+    auto split = [&](int xm, double *z, int &p0, int &p1, int &p2) {
+        const double x = i16_to_unit(xm);
+        const double lo = bw_step1<1>(la11, la21, z[2], z[3], bw_step<1>(lb0, la10, la20, z[0], z[1], x));
+        const double hi = bw_step1<-1>(ha11, ha21, z[6], z[7], bw_step<-1>(hb0, ha10, ha20, z[4], z[5], x));
+        const double mid = __dsub_rn(__dsub_rn(x, lo), hi);
+        p0 = to_pcm_f64(lo); p1 = to_pcm_f64(mid); p2 = to_pcm_f64(hi);
+    };
+
+    const uint4 *src = reinterpret_cast<const uint4 *>(pre) + (g0f >> 2);
+    uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
+    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // keep the zero state until the chunk starts
+    if (g0f + 1 < job.chunk_begin) cur.y = 0;
+    if (g0f + 2 < job.chunk_begin) cur.z = 0;
+    if (n_it > 1) nxt = ldg16(src + 1);
+    for (int it = 0; it < n_it; ++it) {
         uint4 nn = nxt;
-        if (it + 2 < gr.n) nn = ldg16(src + it + 2);
-        const int64_t g = gr.g0 + 4 * (int64_t)it;
+        if (it + 2 < n_it) nn = ldg16(src + it + 2);
+        const int64_t g = g0f + 4 * (int64_t)it;
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o0[4], o1[4], o2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int xm = ch ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu);
-            const double x = i16_to_f64(xm) * (1.0 / 32768.0);
-            const double lo = bw_step1<1>(la11, la21, z[2], z[3], bw_step<1>(lb0, la10, la20, z[0], z[1], x));
-            const double hi = bw_step1<-1>(ha11, ha21, z[6], z[7], bw_step<-1>(hb0, ha10, ha20, z[4], z[5], x));
-            const double mid = __dsub_rn(__dsub_rn(x, lo), hi);
-            const int p0 = to_pcm_f64(lo), p1 = to_pcm_f64(mid), p2 = to_pcm_f64(hi);
-            // pack this lane's three band samples, exchange with the other channel in two shuffles
-            const uint32_t a = pack16(p0, p1);
-            const uint32_t qa = __shfl_xor_sync(kFull, a, 1);
-            const int q2 = __shfl_xor_sync(kFull, p2, 1);
-            const int q0 = (int16_t)(qa & 0xffffu), q1 = (int16_t)(qa >> 16);
-            o0[k] = ch ? pack16(q0, p0) : pack16(p0, q0);
-            o1[k] = ch ? pack16(q1, p1) : pack16(p1, q1);
-            o2[k] = ch ? pack16(q2, p2) : pack16(p2, q2);
+            int l0, l1, l2, r0, r1, r2;
+            split((int)(int16_t)(w[k] & 0xffffu), zl, l0, l1, l2);
+            split((int)(int16_t)(w[k] >> 16), zr, r0, r1, r2);
+            o0[k] = pack16(l0, r0); o1[k] = pack16(l1, r1); o2[k] = pack16(l2, r2);
         }
-        if (it < gr.n) {
-            if (g >= job.tile_begin && g + 4 <= f_hi) {
-                // L lane stores low and high, R lane stores mid: spread the store traffic over the pair
-                if (ch == 0) {
-                    *reinterpret_cast<uint4 *>(b0 + g) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-                    *reinterpret_cast<uint4 *>(b2 + g) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-                } else {
-                    *reinterpret_cast<uint4 *>(b1 + g) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-                }
-            } else if (ch == 0) {
+        if (g >= job.tile_begin && g + 4 <= f_hi) {
+            *reinterpret_cast<uint4 *>(b0 + g) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<uint4 *>(b1 + g) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<uint4 *>(b2 + g) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (g + k >= job.tile_begin && g + k < f_hi) { b0[g + k] = o0[k]; b1[g + k] = o1[k]; b2[g + k] = o2[k]; }
-            }
+            for (int k = 0; k < 4; ++k)
+                if (g + k >= job.tile_begin && g + k < f_hi) { b0[g + k] = o0[k]; b1[g + k] = o1[k]; b2[g + k] = o2[k]; }
         }
         cur = nxt; nxt = nn;
     }
@@ -730,18 +697,15 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg
 // k_kweight_energy: s16 -> x/32768 -> BS.1770 pre-filter + RLB (2 biquads, FP64) -> sum of squares
 // per 100 ms sub-block (ebur128.c filter + gating-block sums).  K-filter state runs through the
 // whole track (the reference measures the concatenated file), so warm-up may cross chunk joins.
-// Each lane adds its channel's sub-block sum with one atomicAdd (two addends per slot on a zeroed
-// array: order-independent, hence deterministic).
+// One thread per tile of sub-blocks, both channels (two independent chains).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
                  const TrackDev *__restrict__ tdev, const int16_t *__restrict__ pre,
                  double *__restrict__ energy, int *__restrict__ peak) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pair = tid >> 1;
-    if (pair >= n_jobs) return;
-    const int ch = tid & 1;
-    const KwJob job = jobs[pair];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const KwJob job = jobs[j];
     const ame_track_params *tp = tracks + job.track;
     const TrackDev td = tdev[job.track];
     const ame_biquad k0 = tp->kw[0], k1 = tp->kw[1];
@@ -752,33 +716,35 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
     int64_t f_lo = t_begin - (int64_t)tp->warm_kw;
     if (f_lo < 0) f_lo = 0;
     f_lo &= ~(int64_t)3;                                         // extra warm-up frames are harmless
-    double z0 = 0, z1 = 0, z2 = 0, z3 = 0, acc = 0;
+    double zl[4] = {0, 0, 0, 0}, zr[4] = {0, 0, 0, 0}, accl = 0, accr = 0;
     int pk = 0;
     int64_t next_end = t_begin + s100;
     int sb = job.sb_begin;
     const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(pre) + base + f_lo);
-    uint4 cur = ldg16(src);
-    for (int64_t g = f_lo; g < t_end; g += 4) {
-        ++src;
-        uint4 nxt = cur;
-        if (g + 4 < t_end) nxt = ldg16(src);
+    uint4 cur = ldg16(src), nxt = cur;
+    if (f_lo + 4 < t_end) nxt = ldg16(src + 1);
+    src += 2;
+    for (int64_t g = f_lo; g < t_end; g += 4, ++src) {
+        uint4 nn = nxt;
+        if (g + 8 < t_end) nn = ldg16(src);
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t f = g + k;
-            const int xm = ch ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu);
-            const double x = i16_to_f64(xm) * (1.0 / 32768.0);
-            const double y = bq_step(k1, z2, z3, bq_step(k0, z0, z1, x));
+            const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
+            const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
+            const double yr = bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
             if (f >= t_begin && f < t_end) {
-                acc = fma(y, y, acc);
-                pk = max(pk, abs(xm));
+                accl = fma(yl, yl, accl);
+                accr = fma(yr, yr, accr);
+                pk = max(pk, max(abs(xl), abs(xr)));
                 if (f + 1 == next_end) {
-                    atomicAdd(energy + td.sb_offset + sb, acc);
-                    acc = 0; ++sb; next_end += s100;
+                    energy[td.sb_offset + sb] = accl + accr;     // ebur128: per-channel sums, then added
+                    accl = 0; accr = 0; ++sb; next_end += s100;
                 }
             }
         }
-        cur = nxt;
+        cur = nxt; nxt = nn;
     }
     atomicMax(peak + job.track, pk);
 }
