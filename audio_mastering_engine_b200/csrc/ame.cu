@@ -121,7 +121,7 @@ int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
     return AME_OK;
 }
 
-// split chunk [cb, ce) into ceil(n / T) near-equal tiles whose interior boundaries are multiples of 4
+// split chunk [cb, ce) into ceil(n / T) near-equal tiles whose interior boundaries are multiples of 8
 void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T) {
     const int64_t n = ce - cb;
     if (n <= 0) return;
@@ -129,7 +129,7 @@ void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, in
     const int64_t t = align_up((n + k - 1) / k, 8);
     int64_t b = cb;
     while (b < ce) {
-        int64_t e = (b + t) & ~(int64_t)3;
+        int64_t e = (b + t) & ~(int64_t)7;
         if (e <= b) e = b + t;
         if (e > ce) e = ce;
         out.push_back(TileJob{cb, b, e, track, variant});
@@ -304,9 +304,17 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)pick_tile(chunks_all, p->eq_slots, kMinTile);
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8)
                                             : (int)pick_tile(chunks_mb, p->split_slots, kMinTile);
-    const int64_t kw_slots = (int64_t)n_sm * 16 * 128;
-    if (o.kw_tile_subblocks > 0) p->kw_tile_sb = o.kw_tile_subblocks;
-    else p->kw_tile_sb = (int)std::max<int64_t>(1, (p->n_sb_total + kw_slots - 1) / kw_slots);
+    if (o.kw_tile_subblocks > 0) {
+        p->kw_tile_sb = o.kw_tile_subblocks;
+    } else {
+        // a tile of sub-blocks costs (tile + warm-up) frames: keep the warm-up below ~15 % when the batch is big
+        // enough to still give every SM ~512 threads, else shrink the tile towards one sub-block
+        int max_warm = 0, min_s100 = 1 << 30;
+        for (int t = 0; t < n_tracks; ++t) { max_warm = std::max(max_warm, p->tracks[t].warm_kw); min_s100 = std::min(min_s100, p->tdev[t].s100); }
+        const int64_t want = std::max<int64_t>(1, ((int64_t)max_warm * 6 + min_s100 - 1) / min_s100);
+        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / ((int64_t)n_sm * 512));
+        p->kw_tile_sb = (int)std::min(want, fill);
+    }
 
     // ---- job tables ---------------------------------------------------------------------------
     std::vector<TileJob> eq_jobs, split_jobs;

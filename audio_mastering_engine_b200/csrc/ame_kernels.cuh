@@ -296,8 +296,8 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
     if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
     const int64_t f_hi = job.tile_end;
     if (f_hi <= f_lo) return;
-    const int64_t g0f = f_lo & ~(int64_t)3;
-    const int n_it = (int)((f_hi - g0f + 3) >> 2);
+    const int64_t g0f = f_lo & ~(int64_t)7;                // 8 frames = one 32-byte sector per iteration
+    const int n_it = (int)((f_hi - g0f + 7) >> 3);
     uint32_t *b0 = reinterpret_cast<uint32_t *>(bands) + delta;
     uint32_t *b1 = b0 + mb_frames;
     uint32_t *b2 = b1 + mb_frames;
@@ -311,34 +311,40 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
     };
 
     const uint4 *src = reinterpret_cast<const uint4 *>(pre) + (g0f >> 2);
-    uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
-    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // keep the zero state until the chunk starts
-    if (g0f + 1 < job.chunk_begin) cur.y = 0;
-    if (g0f + 2 < job.chunk_begin) cur.z = 0;
-    if (n_it > 1) nxt = ldg16(src + 1);
-    for (int it = 0; it < n_it; ++it) {
-        uint4 nn = nxt;
-        if (it + 2 < n_it) nn = ldg16(src + it + 2);
-        const int64_t g = g0f + 4 * (int64_t)it;
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        uint32_t o0[4], o1[4], o2[4];
+    uint4 c0 = ldg16(src), c1 = ldg16(src + 1), n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    {   // keep the zero state until the chunk starts
+        uint32_t *cw0 = reinterpret_cast<uint32_t *>(&c0), *cw1 = reinterpret_cast<uint32_t *>(&c1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            if (g0f + k < job.chunk_begin) cw0[k] = 0;
+            if (g0f + 4 + k < job.chunk_begin) cw1[k] = 0;
+        }
+    }
+    if (n_it > 1) { n0 = ldg16(src + 2); n1 = ldg16(src + 3); }
+    for (int it = 0; it < n_it; ++it) {
+        uint4 m0 = n0, m1 = n1;
+        if (it + 2 < n_it) { m0 = ldg16(src + 2 * it + 4); m1 = ldg16(src + 2 * it + 5); }
+        const int64_t g = g0f + 8 * (int64_t)it;
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        uint32_t o0[8], o1[8], o2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
             int l0, l1, l2, r0, r1, r2;
             split((int)(int16_t)(w[k] & 0xffffu), zl, l0, l1, l2);
             split((int)(int16_t)(w[k] >> 16), zr, r0, r1, r2);
             o0[k] = pack16(l0, r0); o1[k] = pack16(l1, r1); o2[k] = pack16(l2, r2);
         }
-        if (g >= job.tile_begin && g + 4 <= f_hi) {
-            *reinterpret_cast<uint4 *>(b0 + g) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-            *reinterpret_cast<uint4 *>(b1 + g) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-            *reinterpret_cast<uint4 *>(b2 + g) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        if (g >= job.tile_begin && g + 8 <= f_hi) {
+            uint4 *q0 = reinterpret_cast<uint4 *>(b0 + g), *q1 = reinterpret_cast<uint4 *>(b1 + g), *q2 = reinterpret_cast<uint4 *>(b2 + g);
+            q0[0] = make_uint4(o0[0], o0[1], o0[2], o0[3]); q0[1] = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+            q1[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]); q1[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+            q2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]); q2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 8; ++k)
                 if (g + k >= job.tile_begin && g + k < f_hi) { b0[g + k] = o0[k]; b1[g + k] = o1[k]; b2[g + k] = o2[k]; }
         }
-        cur = nxt; nxt = nn;
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1;
     }
 }
 
@@ -655,31 +661,42 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg
     const int64_t lseg = seg - ck.seg_prefix;
     const int64_t f0 = lseg * kSeg;
     const int64_t n = ck.n;
-    int accl[8], accr[8];
+    // issue every load of the segment first (24 groups x {rms, band word, entry attenuation}): the kernel is
+    // bound by memory latency, not by arithmetic
+    unsigned rv[3][8];
+    uint32_t wv[3][8];
+    double ce[3][8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)b * mb_frames + ck.mb_begin;
         const uint16_t *rp = rms + (int64_t)b * mb_frames + ck.mb_begin;
-        const double *ap = att_f + (int64_t)b * mb_frames + ck.mb_begin;
         const double *cp = ckpt + ck.ck_begin[b] + lseg * 8;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int64_t i = f0 + g * 32 + lane;
+            const bool valid = i < n;
+            rv[b][g] = valid ? (unsigned)__ldg(rp + i) : 0u;
+            wv[b][g] = valid ? __ldg(bp + i) : 0u;
+            ce[b][g] = (f0 + g * 32 < n) ? __ldg(cp + g) : 0.0;
+        }
+    }
+    int accl[8], accr[8];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const double *ap = att_f + (int64_t)b * mb_frames + ck.mb_begin;
         double c_att = 0.0, c_fac = 1.0;           // per-lane cache of the last gain computed
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const int64_t i = f0 + g * 32 + lane;
-            int l = 0, r = 0;
-            if (f0 + g * 32 < n) {                 // warp-uniform
-                const bool valid = i < n;
-                const unsigned rv = valid ? (unsigned)__ldg(rp + i) : 0u;
-                const uint32_t w = valid ? __ldg(bp + i) : 0u;
-                const unsigned flags = __ballot_sync(kFull, rv != 0);
-                const unsigned below = flags & (0xffffffffu >> (31 - lane));
-                const double mine = below ? __ldg(ap + (i - lane) + (31 - __clz(below))) : __ldg(cp + g);
-                l = (int16_t)(w & 0xffffu); r = (int16_t)(w >> 16);
-                if (mine != 0.0) {
-                    if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
-                    l = mul_floor(l, c_fac);
-                    r = mul_floor(r, c_fac);
-                }
+            const uint32_t w = wv[b][g];
+            int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
+            const unsigned flags = __ballot_sync(kFull, rv[b][g] != 0);
+            const unsigned below = flags & (0xffffffffu >> (31 - lane));
+            const double mine = below ? __ldg(ap + (i - lane) + (31 - __clz(below))) : ce[b][g];
+            if (mine != 0.0) {
+                if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
+                l = mul_floor(l, c_fac);
+                r = mul_floor(r, c_fac);
             }
             accl[g] = b ? sat16(accl[g] + l) : l;
             accr[g] = b ? sat16(accr[g] + r) : r;
@@ -715,21 +732,22 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
     const int64_t t_end = (int64_t)job.sb_end * s100;
     int64_t f_lo = t_begin - (int64_t)tp->warm_kw;
     if (f_lo < 0) f_lo = 0;
-    f_lo &= ~(int64_t)3;                                         // extra warm-up frames are harmless
+    f_lo &= ~(int64_t)7;                                         // extra warm-up frames are harmless
     double zl[4] = {0, 0, 0, 0}, zr[4] = {0, 0, 0, 0}, accl = 0, accr = 0;
     int pk = 0;
     int64_t next_end = t_begin + s100;
     int sb = job.sb_begin;
     const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(pre) + base + f_lo);
-    uint4 cur = ldg16(src), nxt = cur;
-    if (f_lo + 4 < t_end) nxt = ldg16(src + 1);
-    src += 2;
-    for (int64_t g = f_lo; g < t_end; g += 4, ++src) {
-        uint4 nn = nxt;
-        if (g + 8 < t_end) nn = ldg16(src);
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+    const int n_it = (int)((t_end - f_lo + 7) >> 3);             // 8 frames = one 32-byte sector per iteration
+    uint4 c0 = ldg16(src), c1 = ldg16(src + 1), n0 = c0, n1 = c1;
+    if (n_it > 1) { n0 = ldg16(src + 2); n1 = ldg16(src + 3); }
+    for (int it = 0; it < n_it; ++it) {
+        uint4 m0 = n0, m1 = n1;
+        if (it + 2 < n_it) { m0 = ldg16(src + 2 * it + 4); m1 = ldg16(src + 2 * it + 5); }
+        const int64_t g = f_lo + 8 * (int64_t)it;
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
             const int64_t f = g + k;
             const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
             const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
@@ -744,7 +762,7 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
                 }
             }
         }
-        cur = nxt; nxt = nn;
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1;
     }
     atomicMax(peak + job.track, pk);
 }
