@@ -27,7 +27,7 @@ class CompBand(C.Structure):
 
 
 class TrackParams(C.Structure):
-    _fields_ = [("offset_frames", C.c_int64), ("n_frames", C.c_int64), ("sample_rate", C.c_int32),
+    _fields_ = [("offset_frames", C.c_int64), ("n_frames", C.c_int64), ("halo_frames", C.c_int64), ("sample_rate", C.c_int32),
                 ("chunk_frames", C.c_int32), ("flags", C.c_uint32), ("warm_lut", C.c_int32),
                 ("wl_b0", C.c_double), ("wl_b1", C.c_double), ("wl_a1", C.c_double), ("wl_gm1", C.c_double),
                 ("wh_b0", C.c_double), ("wh_b1", C.c_double), ("wh_a1", C.c_double), ("wh_gm1", C.c_double),

@@ -171,6 +171,8 @@ int64_t pick_tile(const std::vector<std::vector<int64_t>> &chunks_per_track, int
 int validate(const ame_track_params &t, int idx) {
     if (t.n_frames < 0 || t.offset_frames < 0 || (t.offset_frames & 7))
         return fail(AME_E_INVALID, "track %d: offset_frames must be a non-negative multiple of 8", idx);
+    if (t.halo_frames < 0 || (t.halo_frames & 7) || (t.sample_rate > 0 && t.halo_frames % ((t.sample_rate + 5) / 10)))
+        return fail(AME_E_INVALID, "track %d: halo_frames must be a multiple of 8 and of the 100 ms sub-block", idx);
     if (t.sample_rate < 8000 || t.sample_rate > 384000)
         return fail(AME_E_INVALID, "track %d: unsupported sample rate %d", idx, t.sample_rate);
     if (t.warm_eq < 0 || t.warm_xover < 0 || t.warm_kw < 0)
@@ -263,19 +265,24 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     for (int t = 0; t < n_tracks; ++t) {
         ame_track_params &tp = p->tracks[t];
         if ((rc = validate(tp, t)) != AME_OK) return bail(rc);
-        spans.emplace_back(tp.offset_frames, tp.offset_frames + tp.n_frames);
-        p->total_frames = std::max(p->total_frames, align_up(tp.offset_frames + tp.n_frames, 8));
+        const int64_t n_total = tp.halo_frames + tp.n_frames;
+        spans.emplace_back(tp.offset_frames, tp.offset_frames + n_total);
+        p->total_frames = std::max(p->total_frames, align_up(tp.offset_frames + n_total, 8));
         sum_frames += tp.n_frames;
         if (tp.flags & AME_F_MULTIBAND) {
             p->mb_offset[t] = p->mb_frames;
-            p->mb_frames += align_up(tp.n_frames, 8);
+            p->mb_frames += align_up(n_total, 8);
             sum_mb += tp.n_frames;
             for (int b = 0; b < 3; ++b) p->max_look = std::max(p->max_look, tp.comp[b].look_frames);
         }
         if (tp.flags & AME_F_NORMALIZE) p->any_normalize = true;
         const int s100 = (tp.sample_rate + 5) / 10;
         p->tdev[t].s100 = s100;
-        p->tdev[t].n_sb = (int)(tp.n_frames / s100);
+        p->tdev[t].n_sb = (int)(n_total / s100);
+        p->tdev[t].n_total = n_total;
+        p->tdev[t].pad = 0;
+        // blocks whose last sub-block lies in the halo were counted by the previous shard
+        p->tdev[t].first_block = tp.halo_frames ? std::max<int>(0, (int)(tp.halo_frames / s100) - 3) : 0;
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
     }
@@ -374,11 +381,11 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         }
         int64_t c0 = 0;
         for (int64_t cn : chunks_all[t]) {
-            const int64_t cb = tp.offset_frames + c0, ce = cb + cn;
+            const int64_t cb = tp.offset_frames + tp.halo_frames + c0, ce = cb + cn;
             tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
             if (mb) {
                 tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
-                MbChunk ck{cb, p->mb_offset[t] + c0, cn, p->n_seg_total, {0, 0, 0}, t, 0};
+                MbChunk ck{cb, p->mb_offset[t] + tp.halo_frames + c0, cn, p->n_seg_total, {0, 0, 0}, t, 0};
                 for (int b = 0; b < 3; ++b) {
                     const double thr = tp.comp[b].thresh_rms;
                     const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
@@ -394,7 +401,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
             kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
         for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
-            gain_jobs.push_back(GainJob{tp.offset_frames + b, tp.offset_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
+            gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
+                                        tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
     }
     // longest chains first: the sequential compressor kernel is bounded by its slowest warp
     std::stable_sort(chain_jobs.begin(), chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });

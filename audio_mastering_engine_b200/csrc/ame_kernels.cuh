@@ -47,8 +47,11 @@ struct AttEntry { double m, inc, dec, tau; };
 
 struct TrackDev {          // device-side per-track bookkeeping
     int64_t sb_offset;     // start of this track's 100 ms energies in the energy array
-    int32_t n_sb;          // number of complete 100 ms sub-blocks
+    int32_t n_sb;          // number of complete 100 ms sub-blocks (halo included)
     int32_t s100;          // frames per 100 ms = (fs + 5) / 10   (ebur128.c)
+    int32_t first_block;   // time shards: 400 ms blocks before this one belong to the previous shard / the warm-up
+    int32_t pad;
+    int64_t n_total;       // halo + span frames
 };
 
 __constant__ double c_hist_bounds[1001];
@@ -775,7 +778,7 @@ __global__ void k_tail_peak(const ame_track_params *__restrict__ tracks, const T
     const int64_t begin = (int64_t)tdev[t].n_sb * tdev[t].s100;
     const int16_t *p = pre + 2 * tracks[t].offset_frames;
     int pk = 0;
-    for (int64_t i = 2 * begin + threadIdx.x; i < 2 * tracks[t].n_frames; i += blockDim.x) pk = max(pk, abs((int)p[i]));
+    for (int64_t i = 2 * begin + threadIdx.x; i < 2 * tdev[t].n_total; i += blockDim.x) pk = max(pk, abs((int)p[i]));
     atomicMax(peak + t, pk);
 }
 
@@ -798,7 +801,7 @@ k_block_hist(const TrackDev *__restrict__ tdev, const double *__restrict__ energ
     const TrackDev td = tdev[t];
     const double *e = energy + td.sb_offset;
     const double denom = (double)(4 * (int64_t)td.s100);
-    for (int j = threadIdx.x; j + 3 < td.n_sb; j += blockDim.x) {
+    for (int j = td.first_block + threadIdx.x; j + 3 < td.n_sb; j += blockDim.x) {
         const double s = (((e[j] + e[j + 1]) + e[j + 2]) + e[j + 3]) / denom;
         if (s >= c_hist_bounds[0]) atomicAdd(&s_hist[hist_index(s)], 1u);
     }

@@ -164,12 +164,13 @@ def warm_lut(analog_character):
     return np.tanh(x * drive).astype(np.float32, copy=False)
 
 
-def track_params(settings, fs, n_frames, offset_frames=0, chunk_seconds=30, lut_index=None):
+def track_params(settings, fs, n_frames, offset_frames=0, chunk_seconds=30, lut_index=None, halo_frames=0):
     """Fill one ame_track_params from a reference-style settings dict.  `lut_index` maps
     analog_character -> table index and is extended in place."""
     fs = int(fs)
     p = L.TrackParams()
     p.offset_frames, p.n_frames, p.sample_rate = int(offset_frames), int(n_frames), fs
+    p.halo_frames = int(halo_frames)
     p.chunk_frames = int(chunk_seconds * fs) if chunk_seconds else 0
     flags = 0
     p.warm_lut = -1

@@ -39,7 +39,7 @@ class MasterPlan:
     """
 
     def __init__(self, lengths, sample_rates, settings_list, device=0, chunk_seconds=30, host_io=False,
-                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0):
+                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None):
         self.lib = L.load()
         n = len(lengths)
         if n == 0:
@@ -51,15 +51,17 @@ class MasterPlan:
         self.lengths = [int(x) for x in lengths]
         self.sample_rates = [int(x) for x in sample_rates]
         self.settings = list(settings_list)
+        # time shards carry `halo` frames of the previous shard's pre-normalisation tail in front of their span
+        self.halos = [0] * n if halos is None else [int(h) for h in halos]
         self.offsets, off = [], 0
-        for ln in self.lengths:
+        for ln, h in zip(self.lengths, self.halos):
             self.offsets.append(off)
-            off += _align8(ln)
+            off += _align8(ln + h)
         lut_index = {}
         arr = (L.TrackParams * n)()
         for i in range(n):
             arr[i] = design.track_params(self.settings[i], self.sample_rates[i], self.lengths[i], self.offsets[i],
-                                         chunk_seconds, lut_index)
+                                         chunk_seconds, lut_index, self.halos[i])
         self.params = arr
         opt = L.PlanOptions(int(eq_tile_frames), int(xover_tile_frames), int(kw_tile_subblocks), 1 if host_io else 0)
         h = C.c_void_p()
@@ -92,12 +94,13 @@ class MasterPlan:
         """list of int16[N_i,2] -> one packed int16[total_frames,2] host array."""
         if out is None:
             out = np.zeros((self.total_frames, 2), dtype=np.int16)
-        for t, off, ln in zip(tracks, self.offsets, self.lengths):
-            out[off:off + ln] = t
+        for t, off, ln, h in zip(tracks, self.offsets, self.lengths, self.halos):
+            out[off + h:off + h + ln] = t
         return out
 
     def unpack(self, packed):
-        return [np.array(packed[off:off + ln], copy=True) for off, ln in zip(self.offsets, self.lengths)]
+        return [np.array(packed[off + h:off + h + ln], copy=True)
+                for off, ln, h in zip(self.offsets, self.lengths, self.halos)]
 
     def results(self):
         out = []

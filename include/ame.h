@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AME_ABI_VERSION 1
+#define AME_ABI_VERSION 2
 #define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
@@ -77,7 +77,11 @@ typedef struct {
 /* Everything the kernels need for one track.  Filled by the host from the reference's settings dict. */
 typedef struct {
     int64_t offset_frames;   /* start of the track in the packed buffers (multiple of 8) */
-    int64_t n_frames;
+    int64_t n_frames;        /* frames this plan masters (for a time shard: the shard's span) */
+    int64_t halo_frames;     /* time shards only: frames stored BEFORE the span, [offset, offset + halo), that hold
+                                the previous shard's already-mastered pre-normalisation tail; they warm the K filter
+                                up and complete the 400 ms blocks that straddle the shard boundary.  A multiple of
+                                8 and of the 100 ms sub-block; 0 for whole tracks */
     int32_t sample_rate;
     int32_t chunk_frames;    /* state-reset period: 30 * fs (:178); <= 0 means the whole track */
     uint32_t flags;          /* AME_F_* */

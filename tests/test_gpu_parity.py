@@ -223,3 +223,20 @@ def test_wav_entry_point_roundtrip(torch_cuda, tmp_path):
     process_audio(dict(settings, input_file=str(tmp_path / "missing.wav")), status.append,
                   lambda a, b: progress.append((a, b)), art.append, tags.append)
     assert status[-1].startswith("Error:") and progress[-1] == (0, 1) and tags == ["Processing failed."]
+
+
+@pytest.mark.parametrize("fs,seconds,chunk,world", [(48000, 9.0, 1.0, 3), (44100, 5.0, 1.0, 2), (96000, 3.0, 0.5, 8)])
+def test_time_sharded_equals_single_plan(torch_cuda, fs, seconds, chunk, world):
+    """Long-track path (BASELINE config C3): shards by time with halo hand-off and a summed histogram must
+    reproduce the single-plan result (bit for bit) and null against the oracle."""
+    from audio_mastering_engine_b200 import master, synth, sharding
+    from oracle import chain
+    x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    s = synth.c2_settings()
+    one, info1 = master(x, fs, s, chunk_seconds=chunk)
+    many, infon = sharding.master_time_sharded_local(x, fs, s, world, chunk_seconds=chunk)
+    assert infon["n_blocks"] == info1["n_blocks"]
+    assert infon["input_i"] == pytest.approx(info1["input_i"], abs=1e-9)
+    assert np.array_equal(one, many)
+    ref, rinfo = chain.master(x, fs, s, chunk_seconds=chunk)
+    assert _lufs_close(infon["input_i"], rinfo["input_i"]) and _maxdiff(many, ref) <= NULL_LSB
