@@ -45,7 +45,7 @@ class TrackResult(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("eq_tile_frames", C.c_int32), ("xover_tile_frames", C.c_int32), ("kw_tile_subblocks", C.c_int32),
-                ("host_io", C.c_int32)]
+                ("host_io", C.c_int32), ("n_waves", C.c_int32)]
 
 
 class AmeError(RuntimeError):
@@ -67,6 +67,7 @@ SYMBOLS = {
     "ame_plan_total_frames": (C.c_int64, [C.c_void_p]),
     "ame_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "ame_plan_launch_count": (C.c_int64, [C.c_void_p]),
+    "ame_plan_wave_count": (C.c_int32, [C.c_void_p]),
     "ame_plan_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ame_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "ame_kernel_name": (C.c_char_p, [C.c_int]),

@@ -1,4 +1,4 @@
-// libame host side: plan construction (job tables, workspace) and the C ABI of include/ame.h.
+// libame host side: plan construction (job tables, workspace, waves) and the C ABI of include/ame.h.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -46,7 +46,23 @@ int upload(T **dptr, const std::vector<T> &v) {
     return AME_OK;
 }
 
-constexpr int kTargetPairs = 148 * 8 * 16;   // lane pairs that fill 148 SMs at 8 warps each
+constexpr int kMaxTimedSteps = 64;
+constexpr int kMaxTimedWaves = 16;
+constexpr int kTimedSlots = kMaxTimedWaves * AME_N_KERNELS;   // per step
+const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_flag", "k_att_chain",
+    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
+enum { S_EQ = 0, S_SPLIT, S_FLAG, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+
+// A wave = a contiguous range of tracks whose jobs are contiguous in every job table.  The device path
+// launches each kernel ONCE over all waves; the host path (ame_master_host) launches wave by wave so the
+// H2D copy of wave w+1 and the D2H copy of wave w-1 overlap the kernels of wave w.
+struct Wave {
+    int track_lo = 0, track_hi = 0;
+    int64_t frame_lo = 0, frame_hi = 0;            // packed-buffer range (multiples of 8 frames)
+    int eq_lo = 0, eq_n = 0, split_lo = 0, split_n = 0, chain_lo = 0, chain_n = 0, wf_lo = 0, wf_n = 0;
+    int chunk_lo = 0, chunk_n = 0, kw_lo = 0, kw_n = 0, gain_lo = 0, gain_n = 0;
+    int64_t seg_lo = 0, seg_hi = 0;
+};
 
 }  // namespace
 
@@ -56,17 +72,14 @@ struct ame_plan {
     std::vector<ame_track_params> tracks;
     std::vector<int64_t> mb_offset;       // per track, -1 if not multiband
     std::vector<TrackDev> tdev;
+    std::vector<Wave> waves;
+    Wave all;                             // the union of all waves
     int64_t total_frames = 0;             // padded
     int64_t mb_frames = 0;                // padded
-    int64_t n_sb_total = 0;
-    int max_look = 0;
-    int n_eq_jobs = 0, n_split_jobs = 0, n_chain_jobs = 0, n_wf_jobs = 0, n_mb_chunks = 0, n_kw_jobs = 0, n_gain_jobs = 0;
-    int eq_slots = 0, split_slots = 0;
-    int64_t n_seg_total = 0, n_group_total = 0;
+    int64_t n_group_total = 0, n_sb_total = 0;
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     size_t ws_bytes = 0;
     int64_t launches = 0;
-    bool any_normalize = false;
     // device
     ame_track_params *d_tracks = nullptr;
     TrackDev *d_tdev = nullptr;
@@ -86,31 +99,33 @@ struct ame_plan {
     long long *d_hist = nullptr;
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
-    cudaStream_t io_stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
+    std::vector<cudaStream_t> s_run;                                    // host path: kernels, one stream per wave
+    std::vector<cudaEvent_t> ev_in, ev_run;                             // per wave
     // optional per-kernel CUDA-event timing (ame_plan_set_timing)
     bool timing = false;
-    int t_step = -1;
-    std::vector<cudaEvent_t> t_ev;        // [kMaxTimedSteps][AME_N_KERNELS][2]
-    std::vector<char> t_used;             // [kMaxTimedSteps][AME_N_KERNELS]
+    int t_step = -1, t_wave = 0;
+    std::vector<cudaEvent_t> t_ev;        // [kMaxTimedSteps][kMaxTimedWaves][AME_N_KERNELS][2]
+    std::vector<char> t_used;             // [kMaxTimedSteps][kMaxTimedWaves][AME_N_KERNELS]
 };
 
-constexpr int kMaxTimedSteps = 64;
-static const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_flag", "k_att_chain",
-    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
-enum { S_EQ = 0, S_SPLIT, S_FLAG, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+namespace {
 
-static inline void t_begin(ame_plan *p, int slot, cudaStream_t s) {
-    if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps)
-        cudaEventRecord(p->t_ev[((size_t)p->t_step * AME_N_KERNELS + slot) * 2], s);
+inline bool t_on(const ame_plan *p) {
+    return p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps && p->t_wave < kMaxTimedWaves;
 }
-static inline void t_end(ame_plan *p, int slot, cudaStream_t s) {
-    if (p->timing && p->t_step >= 0 && p->t_step < kMaxTimedSteps) {
-        cudaEventRecord(p->t_ev[((size_t)p->t_step * AME_N_KERNELS + slot) * 2 + 1], s);
-        p->t_used[(size_t)p->t_step * AME_N_KERNELS + slot] = 1;
+inline size_t t_slot(const ame_plan *p, int kernel) {
+    return ((size_t)p->t_step * kMaxTimedWaves + p->t_wave) * AME_N_KERNELS + kernel;
+}
+inline void t_begin(ame_plan *p, int kernel, cudaStream_t s) {
+    if (t_on(p)) cudaEventRecord(p->t_ev[t_slot(p, kernel) * 2], s);
+}
+inline void t_end(ame_plan *p, int kernel, cudaStream_t s) {
+    if (t_on(p)) {
+        cudaEventRecord(p->t_ev[t_slot(p, kernel) * 2 + 1], s);
+        p->t_used[t_slot(p, kernel)] = 1;
     }
 }
-
-namespace {
 
 int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
     *ptr = nullptr;
@@ -137,28 +152,15 @@ void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, in
     }
 }
 
-// pad a track's job list with empty jobs to a whole number of warps (16 lane pairs)
-void pad_jobs(std::vector<TileJob> &out, size_t track_first) {
-    if (out.size() == track_first) return;
-    TileJob d = out.back();
-    d.tile_begin = d.tile_end;
-    while ((out.size() - track_first) % 16) out.push_back(d);
-}
-
-// smallest tile (multiple of 8, >= min_tile) whose job count, padded per track, fits `slots` lane pairs
-int64_t pick_tile(const std::vector<std::vector<int64_t>> &chunks_per_track, int64_t slots, int64_t min_tile) {
+// smallest tile (multiple of 8, >= min_tile) whose job count fits `slots` threads
+int64_t pick_tile(const std::vector<int64_t> &chunks, int64_t slots, int64_t min_tile) {
     auto count = [&](int64_t T) {
         int64_t jobs = 0;
-        for (const auto &cs : chunks_per_track) {
-            int64_t j = 0;
-            for (int64_t n : cs) j += (n + T - 1) / T;
-            jobs += j;
-        }
+        for (int64_t n : chunks) jobs += (n + T - 1) / T;
         return jobs;
     };
     int64_t lo = min_tile, hi = min_tile;
-    for (const auto &cs : chunks_per_track)
-        for (int64_t n : cs) hi = std::max(hi, align_up(n, 8));
+    for (int64_t n : chunks) hi = std::max(hi, align_up(n, 8));
     if (count(lo) <= slots) return lo;
     while (lo < hi) {                    // count() is non-increasing in T
         const int64_t mid = align_up((lo + hi) / 2, 8);
@@ -171,10 +173,10 @@ int64_t pick_tile(const std::vector<std::vector<int64_t>> &chunks_per_track, int
 int validate(const ame_track_params &t, int idx) {
     if (t.n_frames < 0 || t.offset_frames < 0 || (t.offset_frames & 7))
         return fail(AME_E_INVALID, "track %d: offset_frames must be a non-negative multiple of 8", idx);
-    if (t.halo_frames < 0 || (t.halo_frames & 7) || (t.sample_rate > 0 && t.halo_frames % ((t.sample_rate + 5) / 10)))
-        return fail(AME_E_INVALID, "track %d: halo_frames must be a multiple of 8 and of the 100 ms sub-block", idx);
     if (t.sample_rate < 8000 || t.sample_rate > 384000)
         return fail(AME_E_INVALID, "track %d: unsupported sample rate %d", idx, t.sample_rate);
+    if (t.halo_frames < 0 || (t.halo_frames & 7) || t.halo_frames % ((t.sample_rate + 5) / 10))
+        return fail(AME_E_INVALID, "track %d: halo_frames must be a multiple of 8 and of the 100 ms sub-block", idx);
     if (t.warm_eq < 0 || t.warm_xover < 0 || t.warm_kw < 0)
         return fail(AME_E_INVALID, "track %d: negative warm-up", idx);
     for (int s = 0; s < 4; ++s) {
@@ -209,6 +211,130 @@ int validate(const ame_track_params &t, int idx) {
     return AME_OK;
 }
 
+// pydub: (1 - 1/ratio) * max(20 * math.log(rms / thresh_rms, 10), 0); CPython's two-argument log is
+// log(x) / log(base) on the platform libm.  tau: smallest a >= 0 with fl(a + inc) >= m.
+void build_att_table(AttEntry *e, const ame_comp_band &c) {
+    const double ln10 = std::log(10.0);
+    for (int r = 0; r <= 32768; ++r) {
+        double over = 0.0;
+        if (r != 0) {
+            const double ratio = (double)r / c.thresh_rms;
+            if (ratio != 0.0) {
+                const double db = 20 * (std::log(ratio) / ln10);
+                over = db > 0 ? db : 0.0;
+            }
+        }
+        const double m = c.coef * over;
+        const double inc = m / c.attack_frames;
+        double tau = m - inc;
+        if (!(tau > 0)) tau = 0.0;
+        while (tau > 0 && tau + inc >= m) tau = std::nextafter(tau, -1.0);
+        while (tau + inc < m) tau = std::nextafter(tau, 1e300);
+        e[r] = AttEntry{m, inc, m / c.release_frames, tau};
+    }
+}
+
+#define LAUNCH_CHECK(p)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess) return fail(AME_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+        ++(p)->launches;                                                                           \
+    } while (0)
+
+int check_warmth(const ame_plan *p) {
+    for (int t = 0; t < p->n_tracks; ++t)
+        if (p->tracks[t].flags & AME_F_WARMTH) {
+            const int l = p->tracks[t].warm_lut;
+            if (l < 0 || l >= p->n_luts) return fail(AME_E_INVALID, "track %d needs warmth table %d but %d are set", t, l, p->n_luts);
+        }
+    return AME_OK;
+}
+
+// ---- stage launches over one wave (or over `all`) ------------------------------------------------
+int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cudaStream_t s) {
+    if (!w.eq_n) return AME_OK;
+    t_begin(p, S_EQ, s);
+    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+    LAUNCH_CHECK(p);
+    t_end(p, S_EQ, s);
+    return AME_OK;
+}
+
+int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands, cudaStream_t s) {
+    if (!w.split_n) return AME_OK;
+    t_begin(p, S_SPLIT, s);
+    k_band_split<<<(w.split_n + 127) / 128, 128, 0, s>>>(p->d_split_jobs + w.split_lo, w.split_n, p->d_tracks, p->d_mb_delta,
+                                                         d_pre, d_bands, p->mb_frames);
+    LAUNCH_CHECK(p);
+    t_end(p, S_SPLIT, s);
+    return AME_OK;
+}
+
+int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_pre, cudaStream_t s) {
+    if (!w.chain_n) return AME_OK;
+    t_begin(p, S_FLAG, s);
+    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, d_bands, p->d_rms, p->mb_frames);
+    LAUNCH_CHECK(p);
+    t_end(p, S_FLAG, s);
+    t_begin(p, S_CHAIN, s);
+    k_att_chain<<<(w.chain_n + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, s>>>(
+        p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
+    LAUNCH_CHECK(p);
+    t_end(p, S_CHAIN, s);
+    t_begin(p, S_APPLY, s);
+    k_compress_apply<<<(unsigned)((w.seg_hi - w.seg_lo + 3) / 4), 128, 0, s>>>(p->d_mb_chunks + w.chunk_lo, w.chunk_n, w.seg_lo, w.seg_hi,
+                                                                                d_bands, p->d_rms, p->d_ckpt, p->d_attf, d_pre, p->mb_frames);
+    LAUNCH_CHECK(p);
+    t_end(p, S_APPLY, s);
+    return AME_OK;
+}
+
+int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, cudaStream_t s) {
+    const int nt = w.track_hi - w.track_lo;
+    if (nt <= 0) return AME_OK;
+    CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));
+    if (w.kw_n) {
+        t_begin(p, S_KW, s);
+        k_kweight_energy<<<(w.kw_n + 127) / 128, 128, 0, s>>>(p->d_kw_jobs + w.kw_lo, w.kw_n, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
+        LAUNCH_CHECK(p);
+        t_end(p, S_KW, s);
+    }
+    t_begin(p, S_TAIL, s);
+    k_tail_peak<<<nt, 128, 0, s>>>(p->d_tracks, p->d_tdev, w.track_lo, w.track_hi, d_pre, p->d_peak);
+    LAUNCH_CHECK(p);
+    t_end(p, S_TAIL, s);
+    t_begin(p, S_HIST, s);
+    k_block_hist<<<nt, 256, 0, s>>>(p->d_tdev, w.track_lo, p->d_energy, (long long *)d_hist);
+    LAUNCH_CHECK(p);
+    t_end(p, S_HIST, s);
+    return AME_OK;
+}
+
+int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, cudaStream_t s) {
+    const int nt = w.track_hi - w.track_lo;
+    if (nt <= 0) return AME_OK;
+    t_begin(p, S_FIN, s);
+    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_peak, p->d_results);
+    LAUNCH_CHECK(p);
+    t_end(p, S_FIN, s);
+    if (w.gain_n) {
+        t_begin(p, S_GAIN, s);
+        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, d_pre, d_out);
+        LAUNCH_CHECK(p);
+        t_end(p, S_GAIN, s);
+    }
+    return AME_OK;
+}
+
+int run_chain_of_stages(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out, cudaStream_t s) {
+    int rc;
+    if ((rc = run_eq(p, w, d_in, p->d_pre, s))) return rc;
+    if ((rc = run_split(p, w, p->d_pre, p->d_bands, s))) return rc;
+    if ((rc = run_compress(p, w, p->d_bands, p->d_pre, s))) return rc;
+    if ((rc = run_hist(p, w, p->d_pre, (int64_t *)p->d_hist, s))) return rc;
+    return run_gain(p, w, p->d_pre, (const int64_t *)p->d_hist, d_out, s);
+}
+
 }  // namespace
 
 extern "C" {
@@ -217,6 +343,7 @@ int ame_abi_version(void) { return AME_ABI_VERSION; }
 size_t ame_sizeof_track_params(void) { return sizeof(ame_track_params); }
 size_t ame_sizeof_track_result(void) { return sizeof(ame_track_result); }
 const char *ame_last_error(void) { return g_err.c_str(); }
+const char *ame_kernel_name(int slot) { return (slot >= 0 && slot < AME_N_KERNELS) ? kKernelNames[slot] : ""; }
 
 int ame_device_count(int *count) {
     if (!count) return fail(AME_E_INVALID, "count is NULL");
@@ -233,7 +360,11 @@ void ame_plan_destroy(ame_plan *p) {
                     p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_peak, p->d_results};
     for (void *q : ptrs)
         if (q) cudaFree(q);
-    if (p->io_stream) cudaStreamDestroy(p->io_stream);
+    for (cudaStream_t s : {p->s_in, p->s_out})
+        if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : p->s_run) cudaStreamDestroy(s);
+    for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->ev_run) cudaEventDestroy(e);
     for (cudaEvent_t e : p->t_ev) cudaEventDestroy(e);
     delete p;
 }
@@ -258,24 +389,24 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     auto bail = [&](int code) { ame_plan_destroy(p); return code; };
 
     // ---- layout -------------------------------------------------------------------------------
-    int64_t sum_frames = 0, sum_mb = 0;
     std::vector<std::pair<int64_t, int64_t>> spans;
     p->mb_offset.assign(n_tracks, -1);
     p->tdev.resize(n_tracks);
+    int max_warm_kw = 0, min_s100 = 1 << 30;
+    int64_t sum_frames = 0;
     for (int t = 0; t < n_tracks; ++t) {
         ame_track_params &tp = p->tracks[t];
         if ((rc = validate(tp, t)) != AME_OK) return bail(rc);
         const int64_t n_total = tp.halo_frames + tp.n_frames;
+        if (t && tp.offset_frames < p->tracks[t - 1].offset_frames)
+            return bail(fail(AME_E_INVALID, "tracks must be ordered by offset_frames"));
         spans.emplace_back(tp.offset_frames, tp.offset_frames + n_total);
         p->total_frames = std::max(p->total_frames, align_up(tp.offset_frames + n_total, 8));
         sum_frames += tp.n_frames;
         if (tp.flags & AME_F_MULTIBAND) {
             p->mb_offset[t] = p->mb_frames;
             p->mb_frames += align_up(n_total, 8);
-            sum_mb += tp.n_frames;
-            for (int b = 0; b < 3; ++b) p->max_look = std::max(p->max_look, tp.comp[b].look_frames);
         }
-        if (tp.flags & AME_F_NORMALIZE) p->any_normalize = true;
         const int s100 = (tp.sample_rate + 5) / 10;
         p->tdev[t].s100 = s100;
         p->tdev[t].n_sb = (int)(n_total / s100);
@@ -285,45 +416,72 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         p->tdev[t].first_block = tp.halo_frames ? std::max<int>(0, (int)(tp.halo_frames / s100) - 3) : 0;
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
+        max_warm_kw = std::max(max_warm_kw, tp.warm_kw);
+        min_s100 = std::min(min_s100, s100);
     }
-    std::sort(spans.begin(), spans.end());
     for (size_t i = 1; i < spans.size(); ++i)
         if (spans[i].first < align_up(spans[i - 1].second, 8)) return bail(fail(AME_E_INVALID, "tracks overlap in the packed buffer"));
     if (p->total_frames == 0) p->total_frames = 8;
 
-    // ---- chunk geometry -----------------------------------------------------------------------
-    std::vector<std::vector<int64_t>> chunks_all(n_tracks), chunks_mb;
+    // ---- waves: contiguous track ranges with about equal frames ----------------------------------
+    int n_waves = o.n_waves > 0 ? o.n_waves : 1;
+    n_waves = std::max(1, std::min(n_waves, n_tracks));
+    {
+        p->waves.resize(n_waves);
+        int t = 0;
+        int64_t acc = 0;
+        for (int w = 0; w < n_waves; ++w) {
+            Wave &wv = p->waves[w];
+            wv.track_lo = t;
+            const int64_t target = sum_frames * (w + 1) / n_waves;
+            const int must_leave = n_waves - 1 - w;                 // at least one track for every later wave
+            while (t < n_tracks - must_leave && (t == wv.track_lo || acc + p->tracks[t].n_frames / 2 <= target)) acc += p->tracks[t++].n_frames;
+            if (w == n_waves - 1) t = n_tracks;
+            wv.track_hi = t;
+            wv.frame_lo = p->tracks[wv.track_lo].offset_frames;
+            wv.frame_hi = (wv.track_hi < n_tracks) ? p->tracks[wv.track_hi].offset_frames : p->total_frames;
+        }
+    }
+
+    // ---- chunk geometry, tile sizes -----------------------------------------------------------------
+    // Tiles are sized so that ONE launch fills the machine with one wave of resident threads (no tail wave).
+    // With several plan waves every wave's launch must do so on its own, so the largest wave decides.
+    std::vector<std::vector<int64_t>> chunks_all(n_tracks);
     for (int t = 0; t < n_tracks; ++t) {
         const ame_track_params &tp = p->tracks[t];
         const int64_t cf = tp.chunk_frames > 0 ? tp.chunk_frames : std::max<int64_t>(tp.n_frames, 1);
         for (int64_t c0 = 0; c0 < tp.n_frames; c0 += cf) chunks_all[t].push_back(std::min(cf, tp.n_frames - c0));
-        if (tp.flags & AME_F_MULTIBAND) chunks_mb.push_back(chunks_all[t]);
     }
-
-    // ---- tile sizes: ONE wave of resident lane pairs (no tail wave), else the minimum tile ---------
-    int n_sm = 148, occ_eq = 2, occ_split = 4;
+    int n_sm = 148, occ_eq = 2, occ_split = 3;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
-    p->eq_slots = n_sm * std::max(occ_eq, 1) * 128;      // one thread per tile
-    p->split_slots = n_sm * std::max(occ_split, 1) * 128;
+    const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128;         // one thread per tile
+    const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128;
     constexpr int64_t kMinTile = 512;
-    p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)pick_tile(chunks_all, p->eq_slots, kMinTile);
-    p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8)
-                                            : (int)pick_tile(chunks_mb, p->split_slots, kMinTile);
+    int64_t eq_tile = kMinTile, split_tile = kMinTile;
+    for (const Wave &wv : p->waves) {
+        std::vector<int64_t> ca, cm;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) {
+            ca.insert(ca.end(), chunks_all[t].begin(), chunks_all[t].end());
+            if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
+        }
+        eq_tile = std::max(eq_tile, pick_tile(ca, eq_slots, kMinTile));
+        split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
+    }
+    p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)eq_tile;
+    p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
     if (o.kw_tile_subblocks > 0) {
         p->kw_tile_sb = o.kw_tile_subblocks;
     } else {
         // a tile of sub-blocks costs (tile + warm-up) frames: keep the warm-up below ~15 % when the batch is big
-        // enough to still give every SM ~512 threads, else shrink the tile towards one sub-block
-        int max_warm = 0, min_s100 = 1 << 30;
-        for (int t = 0; t < n_tracks; ++t) { max_warm = std::max(max_warm, p->tracks[t].warm_kw); min_s100 = std::min(min_s100, p->tdev[t].s100); }
-        const int64_t want = std::max<int64_t>(1, ((int64_t)max_warm * 6 + min_s100 - 1) / min_s100);
-        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / ((int64_t)n_sm * 512));
+        // enough to still give every SM ~512 threads per launch, else shrink the tile towards one sub-block
+        const int64_t want = std::max<int64_t>(1, ((int64_t)max_warm_kw * 6 + min_s100 - 1) / min_s100);
+        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / n_waves / ((int64_t)n_sm * 512));
         p->kw_tile_sb = (int)std::min(want, fill);
     }
 
-    // ---- job tables ---------------------------------------------------------------------------
+    // ---- job tables (every table is ordered by track, hence contiguous per wave) ---------------------
     std::vector<TileJob> eq_jobs, split_jobs;
     std::vector<ChainJob> chain_jobs;
     std::vector<WfJob> wf_jobs;
@@ -333,89 +491,80 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     std::vector<int64_t> mb_delta(n_tracks, 0);
     std::vector<AttEntry> tables;
     std::map<std::tuple<double, double, double, double>, int> table_index;
+    int64_t n_seg_total = 0;
 
-    for (int t = 0; t < n_tracks; ++t) {
-        ame_track_params &tp = p->tracks[t];
-        int variant = 0;
-        for (int s = 0; s < 4; ++s)
-            if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
-        if (tp.flags & AME_F_WARMTH) variant |= 16;
-        const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
-        if (mb) {
-            mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
-            for (int b = 0; b < 3; ++b) {
-                ame_comp_band &c = tp.comp[b];
-                auto key = std::make_tuple(c.thresh_rms, c.coef, c.attack_frames, c.release_frames);
-                auto it = table_index.find(key);
-                if (it == table_index.end()) {
-                    const int idx = (int)table_index.size();
-                    table_index[key] = idx;
-                    // pydub: (1 - 1/ratio) * max(20 * math.log(rms / thresh_rms, 10), 0); CPython's
-                    // two-argument log is log(x) / log(base) on the platform libm.
-                    const double ln10 = std::log(10.0);
-                    tables.resize(tables.size() + 32769);
-                    AttEntry *e = tables.data() + (size_t)idx * 32769;
-                    for (int r = 0; r <= 32768; ++r) {
-                        double over = 0.0;
-                        if (r != 0) {
-                            const double ratio = (double)r / c.thresh_rms;
-                            if (ratio != 0.0) {
-                                const double db = 20 * (std::log(ratio) / ln10);
-                                over = db > 0 ? db : 0.0;
-                            }
-                        }
-                        const double m = c.coef * over;
-                        const double inc = m / c.attack_frames;
-                        // tau: smallest a >= 0 with fl(a + inc) >= m (fl(a + inc) is monotone in a)
-                        double tau = m - inc;
-                        if (!(tau > 0)) tau = 0.0;
-                        while (tau > 0 && tau + inc >= m) tau = std::nextafter(tau, -1.0);
-                        while (tau + inc < m) tau = std::nextafter(tau, 1e300);
-                        e[r] = AttEntry{m, inc, m / c.release_frames, tau};
-                    }
-                    c.table = idx;
-                } else {
-                    c.table = it->second;
-                }
-            }
-        }
-        int64_t c0 = 0;
-        for (int64_t cn : chunks_all[t]) {
-            const int64_t cb = tp.offset_frames + tp.halo_frames + c0, ce = cb + cn;
-            tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
+    for (Wave &wv : p->waves) {
+        wv.eq_lo = (int)eq_jobs.size(); wv.split_lo = (int)split_jobs.size(); wv.chain_lo = (int)chain_jobs.size();
+        wv.chunk_lo = (int)mb_chunks.size(); wv.kw_lo = (int)kw_jobs.size(); wv.gain_lo = (int)gain_jobs.size();
+        wv.seg_lo = n_seg_total;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) {
+            ame_track_params &tp = p->tracks[t];
+            int variant = 0;
+            for (int s = 0; s < 4; ++s)
+                if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
+            if (tp.flags & AME_F_WARMTH) variant |= 16;
+            const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
             if (mb) {
-                tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
-                MbChunk ck{cb, p->mb_offset[t] + tp.halo_frames + c0, cn, p->n_seg_total, {0, 0, 0}, t, 0};
+                mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
                 for (int b = 0; b < 3; ++b) {
-                    const double thr = tp.comp[b].thresh_rms;
-                    const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
-                    ck.ck_begin[b] = p->n_group_total;
-                    chain_jobs.push_back(ChainJob{ck.mb_begin, cn, p->n_group_total, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
-                    p->n_group_total += (cn + 31) / 32;
+                    ame_comp_band &c = tp.comp[b];
+                    auto key = std::make_tuple(c.thresh_rms, c.coef, c.attack_frames, c.release_frames);
+                    auto it = table_index.find(key);
+                    if (it == table_index.end()) {
+                        const int idx = (int)table_index.size();
+                        table_index[key] = idx;
+                        tables.resize(tables.size() + 32769);
+                        build_att_table(tables.data() + (size_t)idx * 32769, c);
+                        c.table = idx;
+                    } else {
+                        c.table = it->second;
+                    }
                 }
-                p->n_seg_total += (cn + kSeg - 1) / kSeg;
-                mb_chunks.push_back(ck);
             }
-            c0 += cn;
+            int64_t c0 = 0;
+            for (int64_t cn : chunks_all[t]) {
+                const int64_t cb = tp.offset_frames + tp.halo_frames + c0, ce = cb + cn;
+                tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
+                if (mb) {
+                    tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
+                    MbChunk ck{cb, p->mb_offset[t] + tp.halo_frames + c0, cn, n_seg_total, {0, 0, 0}, t, 0};
+                    for (int b = 0; b < 3; ++b) {
+                        const double thr = tp.comp[b].thresh_rms;
+                        const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
+                        ck.ck_begin[b] = p->n_group_total;
+                        chain_jobs.push_back(ChainJob{ck.mb_begin, cn, p->n_group_total, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
+                        p->n_group_total += (cn + 31) / 32;
+                    }
+                    n_seg_total += (cn + kSeg - 1) / kSeg;
+                    mb_chunks.push_back(ck);
+                }
+                c0 += cn;
+            }
+            for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
+                kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
+            for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
+                gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
+                                            tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
         }
-        for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
-            kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
-        for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
-            gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
-                                        tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
+        // longest chains first inside the wave: the sequential kernel is bounded by its slowest warp
+        std::stable_sort(chain_jobs.begin() + wv.chain_lo, chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
+        wv.wf_lo = (int)wf_jobs.size();
+        for (int c = wv.chain_lo; c < (int)chain_jobs.size(); ++c)
+            for (int64_t tb = 0; tb < chain_jobs[c].n; tb += kWfTile) wf_jobs.push_back(WfJob{c, 0, tb});
+        wv.eq_n = (int)eq_jobs.size() - wv.eq_lo; wv.split_n = (int)split_jobs.size() - wv.split_lo;
+        wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
+        wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
+        wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
     }
-    // longest chains first: the sequential compressor kernel is bounded by its slowest warp
-    std::stable_sort(chain_jobs.begin(), chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
-    for (int c = 0; c < (int)chain_jobs.size(); ++c)
-        for (int64_t tb = 0; tb < chain_jobs[c].n; tb += kWfTile) wf_jobs.push_back(WfJob{c, 0, tb});
-
-    p->n_eq_jobs = (int)eq_jobs.size();
-    p->n_split_jobs = (int)split_jobs.size();
-    p->n_chain_jobs = (int)chain_jobs.size();
-    p->n_wf_jobs = (int)wf_jobs.size();
-    p->n_mb_chunks = (int)mb_chunks.size();
-    p->n_kw_jobs = (int)kw_jobs.size();
-    p->n_gain_jobs = (int)gain_jobs.size();
+    p->all = p->waves.front();
+    {
+        const Wave &l = p->waves.back();
+        Wave &a = p->all;
+        a.track_hi = l.track_hi; a.frame_hi = l.frame_hi;
+        a.eq_n = l.eq_lo + l.eq_n; a.split_n = l.split_lo + l.split_n; a.chain_n = l.chain_lo + l.chain_n;
+        a.wf_n = l.wf_lo + l.wf_n; a.chunk_n = l.chunk_lo + l.chunk_n; a.kw_n = l.kw_lo + l.kw_n;
+        a.gain_n = l.gain_lo + l.gain_n; a.seg_hi = l.seg_hi;
+    }
 
     // ---- device state -------------------------------------------------------------------------
     if ((rc = upload(&p->d_tracks, p->tracks)) || (rc = upload(&p->d_tdev, p->tdev)) || (rc = upload(&p->d_mb_delta, mb_delta)) ||
@@ -435,8 +584,27 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         return bail(rc);
     if (o.host_io) {
         if ((rc = dmalloc(p, (void **)&p->d_in, fb)) || (rc = dmalloc(p, (void **)&p->d_out, fb))) return bail(rc);
-        if (cudaStreamCreateWithFlags(&p->io_stream, cudaStreamNonBlocking) != cudaSuccess)
+        if (cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaStreamCreate failed"));
+    }
+    if (o.host_io || n_waves > 1) {
+        p->ev_in.resize(n_waves);
+        p->ev_run.resize(n_waves);
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically lower = higher priority
+        for (int w = 0; w < n_waves; ++w) {
+            // earlier waves get the higher priority so a wave that is ahead in the pipeline is never starved by
+            // the bulk kernels of the waves behind it
+            cudaStream_t st = nullptr;
+            const int prio = std::max(prio_hi, std::min(prio_lo, prio_hi + w));
+            if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess)
+                return bail(fail(AME_E_CUDA, "cudaStreamCreate failed"));
+            p->s_run.push_back(st);
+            if (cudaEventCreateWithFlags(&p->ev_in[w], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_run[w], cudaEventDisableTiming) != cudaSuccess)
+                return bail(fail(AME_E_CUDA, "cudaEventCreate failed"));
+        }
     }
     if (cudaMemset(p->d_pre, 0, fb) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
     if (p->mb_frames && cudaMemset(p->d_bands, 0, (size_t)p->mb_frames * 12) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
@@ -472,6 +640,7 @@ int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
 int64_t ame_plan_total_frames(const ame_plan *p) { return p ? p->total_frames : 0; }
 size_t ame_plan_workspace_bytes(const ame_plan *p) { return p ? p->ws_bytes : 0; }
 int64_t ame_plan_launch_count(const ame_plan *p) { return p ? p->launches : 0; }
+int32_t ame_plan_wave_count(const ame_plan *p) { return p ? (int32_t)p->waves.size() : 0; }
 const int16_t *ame_plan_tap_pre(const ame_plan *p) { return p->d_pre; }
 const int16_t *ame_plan_tap_bands(const ame_plan *p) { return p->d_bands; }
 const double *ame_plan_tap_subblock_energy(const ame_plan *p) { return p->d_energy; }
@@ -487,129 +656,14 @@ int ame_plan_read_device(ame_plan *p, void *h_dst, const void *d_src, size_t byt
     return AME_OK;
 }
 
-#define LAUNCH_CHECK(p)                                                                            \
-    do {                                                                                           \
-        cudaError_t e_ = cudaGetLastError();                                                       \
-        if (e_ != cudaSuccess) return fail(AME_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
-        ++(p)->launches;                                                                           \
-    } while (0)
-
-static int check_warmth(const ame_plan *p) {
-    for (int t = 0; t < p->n_tracks; ++t)
-        if (p->tracks[t].flags & AME_F_WARMTH) {
-            const int l = p->tracks[t].warm_lut;
-            if (l < 0 || l >= p->n_luts) return fail(AME_E_INVALID, "track %d needs warmth table %d but %d are set", t, l, p->n_luts);
-        }
-    return AME_OK;
-}
-
-int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream) {
-    if (!p || !d_in || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    int rc = check_warmth(p);
-    if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (p->n_eq_jobs) {
-        const int threads = 128, blocks = (p->n_eq_jobs + threads - 1) / threads;
-        t_begin(p, S_EQ, s);
-        k_eq<<<blocks, threads, 0, s>>>(p->d_eq_jobs, p->n_eq_jobs, p->d_tracks, p->d_luts, d_in, d_pre);
-        LAUNCH_CHECK(p);
-        t_end(p, S_EQ, s);
-    }
-    return AME_OK;
-}
-
-int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, void *stream) {
-    if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (p->n_split_jobs) {
-        if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-        const int threads = 128, blocks = (p->n_split_jobs + threads - 1) / threads;
-        t_begin(p, S_SPLIT, s);
-        k_band_split<<<blocks, threads, 0, s>>>(p->d_split_jobs, p->n_split_jobs, p->d_tracks, p->d_mb_delta, d_pre, d_bands, p->mb_frames);
-        LAUNCH_CHECK(p);
-        t_end(p, S_SPLIT, s);
-    }
-    return AME_OK;
-}
-
-int ame_stage_compress(ame_plan *p, int16_t *d_bands, int16_t *d_pre, void *stream) {
-    if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!p->n_chain_jobs) return AME_OK;
-    if (!d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-    t_begin(p, S_FLAG, s);
-    k_window_flag<<<p->n_wf_jobs, kWfThreads, 0, s>>>(p->d_wf_jobs, p->d_chain_jobs, d_bands, p->d_rms, p->mb_frames);
-    LAUNCH_CHECK(p);
-    t_end(p, S_FLAG, s);
-    t_begin(p, S_CHAIN, s);
-    k_att_chain<<<(p->n_chain_jobs + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, s>>>(
-        p->d_chain_jobs, p->n_chain_jobs, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
-    LAUNCH_CHECK(p);
-    t_end(p, S_CHAIN, s);
-    t_begin(p, S_APPLY, s);
-    k_compress_apply<<<(unsigned)((p->n_seg_total + 3) / 4), 128, 0, s>>>(p->d_mb_chunks, p->n_mb_chunks, p->n_seg_total, d_bands,
-                                                                         p->d_rms, p->d_ckpt, p->d_attf, d_pre, p->mb_frames);
-    LAUNCH_CHECK(p);
-    t_end(p, S_APPLY, s);
-    return AME_OK;
-}
-
-int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, void *stream) {
-    if (!p || !d_pre || !d_hist) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(p->d_peak, 0, (size_t)p->n_tracks * 4, s));
-    if (p->n_kw_jobs) {
-        const int threads = 128, blocks = (p->n_kw_jobs + threads - 1) / threads;
-        t_begin(p, S_KW, s);
-        k_kweight_energy<<<blocks, threads, 0, s>>>(p->d_kw_jobs, p->n_kw_jobs, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
-        LAUNCH_CHECK(p);
-        t_end(p, S_KW, s);
-    }
-    t_begin(p, S_TAIL, s);
-        k_tail_peak<<<p->n_tracks, 128, 0, s>>>(p->d_tracks, p->d_tdev, p->n_tracks, d_pre, p->d_peak);
-    LAUNCH_CHECK(p);
-        t_end(p, S_TAIL, s);
-    t_begin(p, S_HIST, s);
-        k_block_hist<<<p->n_tracks, 256, 0, s>>>(p->d_tdev, p->d_energy, (long long *)d_hist);
-    LAUNCH_CHECK(p);
-        t_end(p, S_HIST, s);
-    return AME_OK;
-}
-
-int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out,
-                         ame_track_result *results, void *stream) {
-    if (!p || !d_pre || !d_hist || !d_out) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    t_begin(p, S_FIN, s);
-        k_finalize<<<(p->n_tracks + 63) / 64, 64, 0, s>>>(p->d_tracks, p->n_tracks, (const long long *)d_hist, p->d_peak, p->d_results);
-    LAUNCH_CHECK(p);
-        t_end(p, S_FIN, s);
-    if (p->n_gain_jobs) {
-        t_begin(p, S_GAIN, s);
-        k_apply_gain<<<p->n_gain_jobs, 256, 0, s>>>(p->d_gain_jobs, p->d_results, d_pre, d_out);
-        LAUNCH_CHECK(p);
-        t_end(p, S_GAIN, s);
-    }
-    if (results) {
-        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    return AME_OK;
-}
-
 int ame_plan_set_timing(ame_plan *p, int enable) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
     CU(cudaSetDevice(p->device));
     if (enable && p->t_ev.empty()) {
-        p->t_ev.resize((size_t)kMaxTimedSteps * AME_N_KERNELS * 2);
+        p->t_ev.resize((size_t)kMaxTimedSteps * kTimedSlots * 2);
         for (auto &e : p->t_ev) CU(cudaEventCreate(&e));
     }
-    p->t_used.assign((size_t)kMaxTimedSteps * AME_N_KERNELS, 0);
+    p->t_used.assign((size_t)kMaxTimedSteps * kTimedSlots, 0);
     p->t_step = -1;
     p->timing = enable != 0;
     return AME_OK;
@@ -621,23 +675,64 @@ int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n
     CU(cudaDeviceSynchronize());
     const int steps = std::min(p->t_step + 1, kMaxTimedSteps);
     for (int k = 0; k < AME_N_KERNELS; ++k) { ms_sum[k] = 0; launches[k] = 0; }
-    for (int st = 0; st < steps; ++st)
-        for (int k = 0; k < AME_N_KERNELS; ++k)
-            if (!p->t_used.empty() && p->t_used[(size_t)st * AME_N_KERNELS + k]) {
-                float ms = 0;
-                CU(cudaEventElapsedTime(&ms, p->t_ev[((size_t)st * AME_N_KERNELS + k) * 2], p->t_ev[((size_t)st * AME_N_KERNELS + k) * 2 + 1]));
-                ms_sum[k] += ms;
-                ++launches[k];
-            }
+    for (size_t i = 0; i < (size_t)steps * kTimedSlots && !p->t_used.empty(); ++i)
+        if (p->t_used[i]) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, p->t_ev[i * 2], p->t_ev[i * 2 + 1]));
+            ms_sum[i % AME_N_KERNELS] += ms;
+            ++launches[i % AME_N_KERNELS];
+        }
     if (n_steps) *n_steps = steps;
     return AME_OK;
 }
 
-const char *ame_kernel_name(int slot) { return (slot >= 0 && slot < AME_N_KERNELS) ? kKernelNames[slot] : ""; }
+// ---- stage entry points (one launch over the whole batch) ------------------------------------------
+int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream) {
+    if (!p || !d_in || !d_pre) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    int rc = check_warmth(p);
+    if (rc) return rc;
+    return run_eq(p, p->all, d_in, d_pre, (cudaStream_t)stream);
+}
+
+int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, void *stream) {
+    if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    if (p->all.split_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
+    return run_split(p, p->all, d_pre, d_bands, (cudaStream_t)stream);
+}
+
+int ame_stage_compress(ame_plan *p, int16_t *d_bands, int16_t *d_pre, void *stream) {
+    if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    if (p->all.chain_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
+    return run_compress(p, p->all, d_bands, d_pre, (cudaStream_t)stream);
+}
+
+int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, void *stream) {
+    if (!p || !d_pre || !d_hist) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    return run_hist(p, p->all, d_pre, d_hist, (cudaStream_t)stream);
+}
+
+int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out,
+                         ame_track_result *results, void *stream) {
+    if (!p || !d_pre || !d_hist || !d_out) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = run_gain(p, p->all, d_pre, d_hist, d_out, s);
+    if (rc) return rc;
+    if (results) {
+        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return AME_OK;
+}
 
 int ame_measure_device(ame_plan *p, const int16_t *d_in, int64_t *d_hist, void *stream) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
     p->launches = 0;
+    p->t_wave = 0;
     if (p->timing) ++p->t_step;
     int rc;
     if ((rc = ame_stage_eq(p, d_in, p->d_pre, stream))) return rc;
@@ -653,23 +748,70 @@ int ame_normalize_device(ame_plan *p, const int64_t *d_hist, int16_t *d_out, ame
 
 int ame_master_device(ame_plan *p, const int16_t *d_in, int16_t *d_out, ame_track_result *results, void *stream) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
-    int rc = ame_measure_device(p, d_in, (int64_t *)p->d_hist, stream);
+    if (!d_in || !d_out) return fail(AME_E_INVALID, "NULL argument");
+    const int nw = (int)p->waves.size();
+    if (nw <= 1) {
+        int rc = ame_measure_device(p, d_in, (int64_t *)p->d_hist, stream);
+        if (rc) return rc;
+        return ame_normalize_device(p, (const int64_t *)p->d_hist, d_out, results, stream);
+    }
+    // several waves: fork the caller's stream into one stream per wave and join again, so the latency-bound
+    // sequential compressor kernel of one wave overlaps the bulk kernels of the others
+    CU(cudaSetDevice(p->device));
+    int rc = check_warmth(p);
     if (rc) return rc;
-    return ame_normalize_device(p, (const int64_t *)p->d_hist, d_out, results, stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    p->launches = 0;
+    if (p->timing) ++p->t_step;
+    CU(cudaEventRecord(p->ev_in[0], s));
+    for (int w = 0; w < nw; ++w) {
+        CU(cudaStreamWaitEvent(p->s_run[w], p->ev_in[0], 0));
+        p->t_wave = w;
+        if ((rc = run_chain_of_stages(p, p->waves[w], d_in, d_out, p->s_run[w]))) return rc;
+        CU(cudaEventRecord(p->ev_run[w], p->s_run[w]));
+        CU(cudaStreamWaitEvent(s, p->ev_run[w], 0));
+    }
+    if (results) {
+        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return AME_OK;
 }
 
+// Host buffers: wave w's H2D copy (stream s_in), kernels (its own stream) and D2H copy (s_out) are chained by
+// events, so the copy engines (PCIe is full duplex) and the SMs work on different waves at the same time, and
+// the latency-bound sequential kernel of one wave overlaps the bulk kernels of the others.  Pinned host memory
+// makes the copies truly asynchronous; pageable memory still works, the copies then serialise.
 int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_result *results) {
     if (!p || !h_in || !h_out) return fail(AME_E_INVALID, "NULL argument");
     if (!p->d_in || !p->d_out) return fail(AME_E_INVALID, "plan was created without host_io");
     CU(cudaSetDevice(p->device));
-    const size_t fb = (size_t)p->total_frames * 4;
-    CU(cudaMemcpyAsync(p->d_in, h_in, fb, cudaMemcpyHostToDevice, p->io_stream));
-    int rc = ame_master_device(p, p->d_in, p->d_out, nullptr, p->io_stream);
+    int rc = check_warmth(p);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h_out, p->d_out, fb, cudaMemcpyDeviceToHost, p->io_stream));
+    p->launches = 0;
+    if (p->timing) ++p->t_step;
+    const int nw = (int)p->waves.size();
+    for (int w = 0; w < nw; ++w) {
+        const Wave &wv = p->waves[w];
+        const size_t off = (size_t)wv.frame_lo * 4, bytes = (size_t)(wv.frame_hi - wv.frame_lo) * 4;
+        CU(cudaMemcpyAsync((char *)p->d_in + off, (const char *)h_in + off, bytes, cudaMemcpyHostToDevice, p->s_in));
+        CU(cudaEventRecord(p->ev_in[w], p->s_in));
+    }
+    for (int w = 0; w < nw; ++w) {
+        CU(cudaStreamWaitEvent(p->s_run[w], p->ev_in[w], 0));
+        p->t_wave = w;
+        if ((rc = run_chain_of_stages(p, p->waves[w], p->d_in, p->d_out, p->s_run[w]))) return rc;
+        CU(cudaEventRecord(p->ev_run[w], p->s_run[w]));
+    }
+    for (int w = 0; w < nw; ++w) {
+        const Wave &wv = p->waves[w];
+        const size_t off = (size_t)wv.frame_lo * 4, bytes = (size_t)(wv.frame_hi - wv.frame_lo) * 4;
+        CU(cudaStreamWaitEvent(p->s_out, p->ev_run[w], 0));
+        CU(cudaMemcpyAsync((char *)h_out + off, (const char *)p->d_out + off, bytes, cudaMemcpyDeviceToHost, p->s_out));
+    }
     if (results)
-        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, p->io_stream));
-    CU(cudaStreamSynchronize(p->io_stream));
+        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, p->s_out));
+    CU(cudaStreamSynchronize(p->s_out));
     return AME_OK;
 }
 

@@ -648,14 +648,14 @@ __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fboun
 // group's entry value; gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)), skipped
 // when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
 __global__ void __launch_bounds__(128)
-k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t n_seg_total,
+k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
                  const int16_t *__restrict__ bands, const uint16_t *__restrict__ rms,
                  const double *__restrict__ ckpt, const double *__restrict__ att_f, int16_t *__restrict__ pre,
                  int64_t mb_frames) {
-    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (seg >= n_seg_total) return;
+    const int64_t seg = seg_lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= seg_hi) return;
     const int lane = threadIdx.x & 31;
-    int lo = 0, hi = n_chunks - 1;                 // last chunk with seg_prefix <= seg
+    int lo = 0, hi = n_chunks - 1;                 // last chunk (of this launch's slice) with seg_prefix <= seg
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (chunks[mid].seg_prefix <= seg) lo = mid; else hi = mid - 1;
@@ -772,9 +772,9 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
 
 // tail frames beyond the last complete sub-block still count for the sample peak
 __global__ void k_tail_peak(const ame_track_params *__restrict__ tracks, const TrackDev *__restrict__ tdev,
-                            int n_tracks, const int16_t *__restrict__ pre, int *__restrict__ peak) {
-    const int t = blockIdx.x;
-    if (t >= n_tracks) return;
+                            int track_lo, int track_hi, const int16_t *__restrict__ pre, int *__restrict__ peak) {
+    const int t = track_lo + blockIdx.x;
+    if (t >= track_hi) return;
     const int64_t begin = (int64_t)tdev[t].n_sb * tdev[t].s100;
     const int16_t *p = pre + 2 * tracks[t].offset_frames;
     int pk = 0;
@@ -793,9 +793,9 @@ __device__ __forceinline__ int hist_index(double e) {   // ebur128.c find_histog
 
 // k_block_hist: 400 ms blocks every 100 ms -> 1000-bin histogram (absolute gate = bin floor, -70 LUFS)
 __global__ void __launch_bounds__(256)
-k_block_hist(const TrackDev *__restrict__ tdev, const double *__restrict__ energy, long long *__restrict__ hist) {
+k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__restrict__ energy, long long *__restrict__ hist) {
     __shared__ unsigned s_hist[1000];
-    const int t = blockIdx.x;
+    const int t = track_lo + blockIdx.x;
     for (int i = threadIdx.x; i < 1000; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const TrackDev td = tdev[t];
@@ -810,11 +810,11 @@ k_block_hist(const TrackDev *__restrict__ tdev, const double *__restrict__ energ
 }
 
 // k_finalize: ebur128_gated_loudness + the linear-mode gain of af_loudnorm, one thread per track
-__global__ void k_finalize(const ame_track_params *__restrict__ tracks, int n_tracks,
+__global__ void k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_hi,
                            const long long *__restrict__ hist, const int *__restrict__ peak,
                            ame_track_result *__restrict__ res) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tracks) return;
+    const int t = track_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= track_hi) return;
     const long long *h = hist + (int64_t)t * 1000;
     ame_track_result r;
     r.input_i = -INFINITY; r.measured_i_2dp = -INFINITY; r.gain = 1.0; r.rel_threshold = 0.0;

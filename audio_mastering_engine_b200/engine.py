@@ -39,7 +39,7 @@ class MasterPlan:
     """
 
     def __init__(self, lengths, sample_rates, settings_list, device=0, chunk_seconds=30, host_io=False,
-                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None):
+                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None, n_waves=1):
         self.lib = L.load()
         n = len(lengths)
         if n == 0:
@@ -63,7 +63,8 @@ class MasterPlan:
             arr[i] = design.track_params(self.settings[i], self.sample_rates[i], self.lengths[i], self.offsets[i],
                                          chunk_seconds, lut_index, self.halos[i])
         self.params = arr
-        opt = L.PlanOptions(int(eq_tile_frames), int(xover_tile_frames), int(kw_tile_subblocks), 1 if host_io else 0)
+        opt = L.PlanOptions(int(eq_tile_frames), int(xover_tile_frames), int(kw_tile_subblocks), 1 if host_io else 0,
+                            int(n_waves))
         h = C.c_void_p()
         L.check(self.lib.ame_plan_create(int(device), arr, n, C.byref(opt), C.byref(h)))
         self.handle = h

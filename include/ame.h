@@ -121,6 +121,11 @@ typedef struct {
     int32_t xover_tile_frames;   /* 0 = auto */
     int32_t kw_tile_subblocks;   /* 0 = auto */
     int32_t host_io;             /* 1 = also allocate device in/out buffers for ame_master_host */
+    int32_t n_waves;             /* <= 1: one wave.  > 1: split the batch into that many contiguous groups of tracks;
+                                    each wave runs on its own stream, so the latency-bound sequential compressor kernel
+                                    of one wave overlaps the bulk kernels of the others, and ame_master_host also
+                                    overlaps the H2D copy of wave w+1 and the D2H copy of wave w-1 with the kernels of
+                                    wave w.  Tiles shrink with the wave, so more waves = more filter warm-up work */
 } ame_plan_options;
 
 typedef struct ame_plan ame_plan;
@@ -142,9 +147,12 @@ int ame_plan_set_warm_luts(ame_plan *plan, const float *luts, int32_t n_luts);
 int64_t ame_plan_total_frames(const ame_plan *plan);     /* padded length of the packed buffers */
 size_t ame_plan_workspace_bytes(const ame_plan *plan);
 int64_t ame_plan_launch_count(const ame_plan *plan);      /* kernels launched by the last call */
+int32_t ame_plan_wave_count(const ame_plan *plan);
 
-/* per-kernel device timing with CUDA events on the processing stream (benchmarks): enable, run up to 64
- * ame_master_* / ame_measure_* calls, then read the summed milliseconds and launch counts per kernel. */
+/* per-kernel device timing with CUDA events on the processing stream(s) (benchmarks): enable, run up to 64
+ * ame_master_* / ame_measure_* calls, then read the summed milliseconds and launch counts per kernel (with
+ * several waves every wave's launch is timed on its own stream; overlapping launches share the machine, so
+ * their durations add up to more than the wall time). */
 int ame_plan_set_timing(ame_plan *plan, int enable);
 int ame_plan_kernel_times(ame_plan *plan, double *ms_sum, int64_t *launches, int *n_steps);
 const char *ame_kernel_name(int slot);
@@ -155,7 +163,8 @@ const char *ame_kernel_name(int slot);
  * (may be NULL).  stream is a cudaStream_t (NULL = default stream). */
 int ame_master_device(ame_plan *plan, const int16_t *d_in, int16_t *d_out,
                       ame_track_result *results, void *stream);
-/* same with HOST buffers (pinned or pageable): H2D, the chain, D2H, synchronised on return. */
+/* same with HOST buffers (pinned or pageable): H2D, the chain, D2H - pipelined over the plan's waves -
+ * synchronised on return. */
 int ame_master_host(ame_plan *plan, const int16_t *h_in, int16_t *h_out, ame_track_result *results);
 
 /* two-phase form for tracks that are time-sharded across GPUs: phase 1 stops after the gating

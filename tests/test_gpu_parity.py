@@ -240,3 +240,16 @@ def test_time_sharded_equals_single_plan(torch_cuda, fs, seconds, chunk, world):
     assert np.array_equal(one, many)
     ref, rinfo = chain.master(x, fs, s, chunk_seconds=chunk)
     assert _lufs_close(infon["input_i"], rinfo["input_i"]) and _maxdiff(many, ref) <= NULL_LSB
+
+
+def test_host_path_waves_equal_single_wave(torch_cuda):
+    """ame_master_host pipelines H2D / kernels / D2H over waves of tracks: same bytes as one wave."""
+    from audio_mastering_engine_b200 import master, synth, EQ_PRESETS
+    fs = 48000
+    tracks = [synth.track(1.0 + 0.37 * k, fs, track_id=k, am_hz=2.0) for k in range(7)]
+    sets = [synth.c4_settings(k + 1, EQ_PRESETS) for k in range(7)]
+    a, ia = master(tracks, fs, sets, chunk_seconds=1)
+    for waves in (2, 3, 7, 16):
+        b, ib = master(tracks, fs, sets, chunk_seconds=1, n_waves=waves)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), waves
+        assert [i["input_i"] for i in ia] == [i["input_i"] for i in ib]
