@@ -277,7 +277,7 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
-    k_att_chain<<<(w.chain_n + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, s>>>(
+    k_att_chain<<<w.chain_n, 64, 0, s>>>(
         p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);

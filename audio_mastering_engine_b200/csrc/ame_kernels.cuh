@@ -486,34 +486,84 @@ __device__ __forceinline__ double att_update(double att, double m, double inc, d
     return (rising && !above) ? s : r;
 }
 
-constexpr int kChainWarps = 2;
+constexpr int kChainStages = 2;    // segment buffers in flight between the producer and the consumer warp
 
-// k_att_chain: the strictly sequential part, one warp per (chunk, band).  Per 256-frame segment the lanes
-// compact the table entries of the flagged frames (lane = 8 consecutive frames) into shared memory in time
-// order; the recurrence then runs over that dense queue (operands at consecutive addresses, so the loads
-// pipeline ahead of the dependent DADD -> integer-compare -> select chain).  Outputs: the attenuation after
-// every flagged frame (att_f, sparse writes) and the attenuation entering every 32-frame group (ckpt).
-__global__ void __launch_bounds__(kChainWarps * 32)
+__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// k_att_chain: the strictly sequential part.  One CTA of two warps per (chunk, band):
+//   warp 0, the PRODUCER, walks the 256-frame segments of the rms plane (lane = 8 consecutive frames), compacts the
+//     table entries (M, tau, inc, dec) of the flagged frames into a shared-memory queue in time order, padded to a
+//     multiple of 16 with no-op entries, and later scatters the results (attenuation after every flagged frame ->
+//     att_f, attenuation entering every 32-frame group -> ckpt);
+//   warp 1, the CONSUMER, does nothing but the recurrence over those queues: 16 steps per iteration from two
+//     ping-pong register blocks so the shared-memory loads of the next 8 steps are in flight while the current 8
+//     run - 25 cycles per dependent step on B200 (profiles/micro/att_chain_latency3.cu), and segments without
+//     flagged frames cost it one barrier.
+// The two warps are decoupled by kChainStages buffers and named barriers (full[s]: producer arrives / consumer
+// waits; done[s]: consumer arrives / producer waits).
+__global__ void __launch_bounds__(64)
 k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
             const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
-    // per warp, double buffered: table entries of the flagged frames of one 256-frame segment, compacted in time
-    // order and padded to a multiple of 16 with no-op entries
-    __shared__ double2 s_mt[kChainWarps][2][kSeg + 16];   // (M, tau)
-    __shared__ double2 s_id[kChainWarps][2][kSeg + 16];   // (inc, dec)
-    __shared__ double s_att[kChainWarps][kSeg + 16];      // attenuation after each flagged frame
-    const int wib = threadIdx.x >> 5;
-    const int warp = blockIdx.x * kChainWarps + wib;
-    if (warp >= n_jobs) return;
+    __shared__ double2 s_mt[kChainStages][kSeg + 32];     // (M, tau)   (+16 no-op entries, +8 read-ahead slack)
+    __shared__ double2 s_id[kChainStages][kSeg + 32];     // (inc, dec)
+    __shared__ double s_att[kChainStages][kSeg + 16];     // attenuation after each flagged frame
+    __shared__ double s_att_in[kChainStages];             // attenuation entering the segment
+    __shared__ int s_total[kChainStages];
+    __shared__ uint8_t s_m8[kChainStages][32];            // producer bookkeeping for the scatter
+    __shared__ uint16_t s_off[kChainStages][32];
+    const int job_i = blockIdx.x;
+    if (job_i >= n_jobs) return;
     const int lane = threadIdx.x & 31;
-    const ChainJob job = jobs[warp];
-    double *__restrict__ qa = s_att[wib];
+    const bool producer = threadIdx.x < 32;
+    const ChainJob job = jobs[job_i];
+    const int64_t n = job.n;
+    const int64_t n_seg = (n + kSeg - 1) / kSeg;
+    constexpr int FULL = 1, DONE = 1 + kChainStages;      // named barrier ids (0 is __syncthreads)
+
+    if (!producer) {
+        // ------------------------------------------------------------------ consumer: the recurrence only
+        double att = 0.0;
+        for (int64_t seg = 0; seg < n_seg; ++seg) {
+            const int st = (int)(seg % kChainStages);
+            named_sync(FULL + st);
+            const int total = s_total[st];
+            if (lane == 0) s_att_in[st] = att;
+            if (total) {
+                const double2 *__restrict__ qmt = s_mt[st];
+                const double2 *__restrict__ qid = s_id[st];
+                double *__restrict__ qa = s_att[st];
+                double2 A0[8], A1[8], B0[8], B1[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { A0[k] = qmt[k]; A1[k] = qid[k]; }
+                for (int j0 = 0; j0 < total; j0 += 16) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { B0[k] = qmt[j0 + 8 + k]; B1[k] = qid[j0 + 8 + k]; }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        att = att_update(att, A0[k].x, A1[k].x, A1[k].y, A0[k].y);
+                        qa[j0 + k] = att;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { A0[k] = qmt[j0 + 16 + k]; A1[k] = qid[j0 + 16 + k]; }   // read-ahead (may be slack)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        att = att_update(att, B0[k].x, B1[k].x, B1[k].y, B0[k].y);
+                        qa[j0 + 8 + k] = att;
+                    }
+                }
+            }
+            named_arrive(DONE + st);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- producer: gather, compact, scatter
     const AttEntry *tbl = tables + (size_t)job.table * 32769;
     const uint16_t *rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
     double *af = att_f + (int64_t)job.band * mb_frames + job.mb_begin;
     double *ck = ckpt + job.ck_begin;
-    const int64_t n = job.n;
     const int64_t n_groups = (n + 31) >> 5;
-    const int64_t n_seg = (n + kSeg - 1) / kSeg;
     const bool vec = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
 
     auto load_seg = [&](int64_t seg, uint32_t *h) {     // this lane's 8 rms values as 4 words
@@ -529,111 +579,70 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
                 if (i + k < n) h[k >> 1] |= (uint32_t)__ldg(rp + i + k) << ((k & 1) * 16);
         }
     };
-    struct SegInfo { unsigned m8; int off, total, before_grp; };
-    auto prep = [&](const uint32_t *h) -> SegInfo {     // compaction geometry of a segment
-        SegInfo si;
-        si.m8 = 0;
+    // scatter the results of a finished segment: attenuation after each flagged frame, and entering each group
+    auto flush = [&](int64_t seg) {
+        const int st = (int)(seg % kChainStages);
+        named_sync(DONE + st);
+        const int total = s_total[st];
+        double ge = s_att_in[st];
+        if (total) {
+            const double *qa = s_att[st];
+            const unsigned m8 = s_m8[st][lane];
+            int slot = s_off[st][lane];
+            // flagged frames before group g = exclusive count at lane 4g; lane g (< 8) keeps it
+            const int before_grp = s_off[st][(lane & 7) * 4];
+            if (before_grp) ge = qa[before_grp - 1];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (m8 & (1u << k)) af[seg * kSeg + lane * 8 + k] = qa[slot++];
+        }
+        if (lane < 8 && seg * 8 + lane < n_groups) ck[seg * 8 + lane] = ge;
+    };
+
+    uint32_t cur[4], nx1[4], nx2[4];                   // rms words are fetched two segments ahead
+    load_seg(0, cur);
+    load_seg(1, nx1);
+    for (int64_t seg = 0; seg < n_seg; ++seg) {
+        const int st = (int)(seg % kChainStages);
+        load_seg(seg + 2, nx2);
+        if (seg >= kChainStages) flush(seg - kChainStages);    // also frees stage st
+        unsigned m8 = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if ((h[k >> 1] >> ((k & 1) * 16)) & 0xffffu) si.m8 |= 1u << k;
-        const int cnt = __popc(si.m8);
-        int incl = cnt;
+            if ((cur[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
+        const int cnt = __popc(m8);
+        int incl = cnt;                                // inclusive scan of the per-lane counts
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(kFull, incl, d);
             if (lane >= d) incl += v;
         }
-        si.total = __shfl_sync(kFull, incl, 31);
-        si.off = incl - cnt;
-        // number of flagged frames before group g = exclusive count at lane 4g; lane g keeps it
-        si.before_grp = __shfl_sync(kFull, si.off, (lane & 7) * 4);
-        return si;
-    };
-    double2 e01[8], e23[8];                             // table entries of this lane's flagged frames, in flight
-    auto gather_issue = [&](const uint32_t *h) {
+        const int total = __shfl_sync(kFull, incl, 31);
+        if (total) {
+            double2 *qmt = s_mt[st], *qid = s_id[st];
+            int slot = incl - cnt;
+            s_m8[st][lane] = (uint8_t)m8;
+            s_off[st][lane] = (uint16_t)slot;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const unsigned r = (h[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-            if (r) {
-                e01[k] = __ldg(reinterpret_cast<const double2 *>(tbl + r));
-                e23[k] = __ldg(reinterpret_cast<const double2 *>(tbl + r) + 1);
-            }
-        }
-    };
-    auto gather_commit = [&](int buf, const SegInfo &si) {
-        double2 *qmt = s_mt[wib][buf], *qid = s_id[wib][buf];
-        int slot = si.off;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (si.m8 & (1u << k)) {
-                qmt[slot] = make_double2(e01[k].x, e23[k].y);
-                qid[slot] = make_double2(e01[k].y, e23[k].x);
-                ++slot;
-            }
-        // no-op entries: M < 0 => "above", dec = 0 => att unchanged
-        if (lane < 16) { qmt[si.total + lane] = make_double2(-1.0, 0.0); qid[si.total + lane] = make_double2(0.0, 0.0); }
-    };
-
-    double att = 0.0;
-    uint32_t cur[4], nx1[4], nx2[4];                   // rms words are fetched two segments ahead
-    load_seg(0, cur);
-    load_seg(1, nx1);
-    SegInfo sc = prep(cur);
-    if (sc.total) { gather_issue(cur); gather_commit(0, sc); }
-    __syncwarp();
-    for (int64_t seg = 0; seg < n_seg; ++seg) {
-        const int buf = (int)(seg & 1);
-        load_seg(seg + 2, nx2);
-        const SegInfo sn = prep(nx1);
-        if (sn.total) gather_issue(nx1);               // next segment's table entries fly during this chain
-        const double att_in = att;
-        if (sc.total) {
-            // The recurrence proper: 16 steps per iteration from two ping-pong register blocks, so the shared
-            // memory loads of the next 8 steps are in flight while the current 8 run.  Measured on B200: 25
-            // cycles per dependent step in this shape against 55 when every step reads its operands from shared
-            // memory, and 75 with regime speculation on real signals whose regime flips almost every frame
-            // (profiles/micro/att_chain_latency3.cu).
-            const double2 *__restrict__ qmt = s_mt[wib][buf];
-            const double2 *__restrict__ qid = s_id[wib][buf];
-            double2 A0[8], A1[8], B0[8], B1[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { A0[k] = qmt[k]; A1[k] = qid[k]; }
-            for (int j0 = 0; j0 < sc.total; j0 += 16) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { B0[k] = qmt[j0 + 8 + k]; B1[k] = qid[j0 + 8 + k]; }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    att = att_update(att, A0[k].x, A1[k].x, A1[k].y, A0[k].y);
-                    qa[j0 + k] = att;
-                }
-                if (j0 + 16 < sc.total) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { A0[k] = qmt[j0 + 16 + k]; A1[k] = qid[j0 + 16 + k]; }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    att = att_update(att, B0[k].x, B1[k].x, B1[k].y, B0[k].y);
-                    qa[j0 + 8 + k] = att;
+            for (int k = 0; k < 8; ++k) {
+                const unsigned r = (cur[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                if (r) {
+                    const double2 a = __ldg(reinterpret_cast<const double2 *>(tbl + r));       // (M, inc)
+                    const double2 b = __ldg(reinterpret_cast<const double2 *>(tbl + r) + 1);   // (dec, tau)
+                    qmt[slot] = make_double2(a.x, b.y);
+                    qid[slot] = make_double2(a.y, b.x);
+                    ++slot;
                 }
             }
+            // no-op entries: M < 0 => "above", dec = 0 => att unchanged
+            if (lane < 16) { qmt[total + lane] = make_double2(-1.0, 0.0); qid[total + lane] = make_double2(0.0, 0.0); }
         }
-        if (sn.total) gather_commit(buf ^ 1, sn);
-        __syncwarp();
-        double ge = att_in;                            // lane g (< 8): attenuation entering group g
-        if (sc.total) {
-            // = value after the flagged frames that precede the group in this segment
-            if (sc.before_grp) ge = qa[sc.before_grp - 1];
-            int slot = sc.off;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (sc.m8 & (1u << k)) af[seg * kSeg + lane * 8 + k] = qa[slot++];
-        }
-        if (lane < 8 && seg * 8 + lane < n_groups) ck[seg * 8 + lane] = ge;
-        __syncwarp();                                  // qa is rewritten by the next segment's chain
-        sc = sn;
+        if (lane == 0) s_total[st] = total;
+        named_arrive(FULL + st);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cur[k] = nx1[k]; nx1[k] = nx2[k]; }
     }
+    for (int64_t seg = (n_seg > kChainStages ? n_seg - kChainStages : 0); seg < n_seg; ++seg) flush(seg);
 }
 
 __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
