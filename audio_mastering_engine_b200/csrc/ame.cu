@@ -170,6 +170,52 @@ int64_t pick_tile(const std::vector<int64_t> &chunks, int64_t slots, int64_t min
     return hi;
 }
 
+// k_eq tiles are cost-balanced: a thread's work is about (tile + warm-up) * cost-per-frame, and the cost per
+// frame differs a lot between tracks (no EQ at all ... 4 stages + warmth).  Give every track the tile length
+// that makes (T + warm) * cost equal to one common budget, the smallest budget whose job count fits `slots`.
+double eq_cost_per_frame(const ame_track_params &t) {
+    double c = 24.0;                                    // unpack, convert, pack, store
+    if (t.flags & AME_F_WARMTH) c += 60.0;              // two table look-ups + the 2x2 mix in explicit FP64 ops
+    if (t.flags & AME_F_WIDTH) c += 8.0;
+    if (t.eq[0].kind != AME_EQ_BYPASS) c += 16.0;       // one section + blend, two channels
+    if (t.eq[1].kind != AME_EQ_BYPASS) c += 36.0;       // four sections + blend, two channels
+    if (t.eq[2].kind != AME_EQ_BYPASS) c += 36.0;
+    if (t.eq[3].kind != AME_EQ_BYPASS) c += 16.0;
+    return c;
+}
+
+// k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
+// both variants one after the other.  Every track therefore gets a whole number of warps, in proportion to its
+// cost (frames x cost per frame), and its 32 * warps jobs are spread over its chunks by length.
+std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<double> &cost,
+                                    int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
+    const int n = (int)chunks.size();
+    std::vector<int> warps(n, 0);
+    std::vector<double> weight(n, 0.0);
+    std::vector<int> cap(n, 0);
+    double wsum = 0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        int64_t frames = 0, max_jobs = 0;
+        for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tile); }
+        weight[t] = (double)frames * cost[t];
+        cap[t] = (int)std::max<int64_t>(1, (max_jobs + 31) / 32);
+        wsum += weight[t];
+    }
+    int64_t avail = std::max<int64_t>(t_hi - t_lo, slots / 32);
+    std::vector<std::pair<double, int>> rem;
+    int64_t used = 0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        const double share = wsum > 0 ? avail * weight[t] / wsum : 1.0;
+        warps[t] = std::min(cap[t], std::max(1, (int)share));
+        used += warps[t];
+        rem.emplace_back(share - warps[t], t);
+    }
+    std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+    for (size_t i = 0; i < rem.size() && used < avail; ++i)
+        if (warps[rem[i].second] < cap[rem[i].second]) { ++warps[rem[i].second]; ++used; }
+    return warps;
+}
+
 int validate(const ame_track_params &t, int idx) {
     if (t.n_frames < 0 || t.offset_frames < 0 || (t.offset_frames & 7))
         return fail(AME_E_INVALID, "track %d: offset_frames must be a non-negative multiple of 8", idx);
@@ -459,17 +505,19 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128;         // one thread per tile
     const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128;
     constexpr int64_t kMinTile = 512;
-    int64_t eq_tile = kMinTile, split_tile = kMinTile;
+    int64_t split_tile = kMinTile;
+    std::vector<double> eq_cost(n_tracks);
+    std::vector<int> eq_warps(n_tracks, 1);
+    for (int t = 0; t < n_tracks; ++t) eq_cost[t] = eq_cost_per_frame(p->tracks[t]);
     for (const Wave &wv : p->waves) {
-        std::vector<int64_t> ca, cm;
-        for (int t = wv.track_lo; t < wv.track_hi; ++t) {
-            ca.insert(ca.end(), chunks_all[t].begin(), chunks_all[t].end());
+        std::vector<int64_t> cm;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t)
             if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
-        }
-        eq_tile = std::max(eq_tile, pick_tile(ca, eq_slots, kMinTile));
         split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
+        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, kMinTile);
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
     }
-    p->eq_tile = o.eq_tile_frames > 0 ? (int)align_up(o.eq_tile_frames, 8) : (int)eq_tile;
+    p->eq_tile = 0;
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
     if (o.kw_tile_subblocks > 0) {
         p->kw_tile_sb = o.kw_tile_subblocks;
@@ -521,10 +569,33 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                     }
                 }
             }
+            // k_eq jobs of this track: 32 * warps jobs spread over the chunks by length (or the requested tile)
+            const size_t eq_first = eq_jobs.size();
+            {
+                int64_t c0e = 0;
+                const int64_t want = (int64_t)eq_warps[t] * 32;
+                for (int64_t cn : chunks_all[t]) {
+                    const int64_t cb = tp.offset_frames + tp.halo_frames + c0e, ce = cb + cn;
+                    int64_t T;
+                    if (o.eq_tile_frames > 0) {
+                        T = align_up(o.eq_tile_frames, 8);
+                    } else {
+                        const int64_t jc = std::max<int64_t>(1, want * cn / std::max<int64_t>(tp.n_frames, 1));   // floor: never over `want`
+                        T = std::max<int64_t>(kMinTile, align_up((cn + jc - 1) / jc, 8));
+                    }
+                    tile_jobs(eq_jobs, t, variant, cb, ce, T);
+                    p->eq_tile = std::max<int>(p->eq_tile, (int)T);
+                    c0e += cn;
+                }
+                if (eq_jobs.size() > eq_first) {            // whole warps per track: pad with empty jobs
+                    TileJob d = eq_jobs.back();
+                    d.tile_begin = d.tile_end;
+                    while ((eq_jobs.size() - eq_first) % 32) eq_jobs.push_back(d);
+                }
+            }
             int64_t c0 = 0;
             for (int64_t cn : chunks_all[t]) {
                 const int64_t cb = tp.offset_frames + tp.halo_frames + c0, ce = cb + cn;
-                tile_jobs(eq_jobs, t, variant, cb, ce, p->eq_tile);
                 if (mb) {
                     tile_jobs(split_jobs, t, 0, cb, ce, p->split_tile);
                     MbChunk ck{cb, p->mb_offset[t] + tp.halo_frames + c0, cn, n_seg_total, {0, 0, 0}, t, 0};
