@@ -323,7 +323,7 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
-    k_att_chain<<<w.chain_n, 64, 0, s>>>(
+    k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
         p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);
@@ -679,6 +679,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     }
     if (cudaMemset(p->d_pre, 0, fb) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
     if (p->mb_frames && cudaMemset(p->d_bands, 0, (size_t)p->mb_frames * 12) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
+
+    if (cudaFuncSetAttribute(k_att_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChainsPerCta * sizeof(ChainSmem))) != cudaSuccess)
+        return bail(fail(AME_E_CUDA, "cannot reserve %zu bytes of shared memory for k_att_chain", kChainsPerCta * sizeof(ChainSmem)));
 
     // ebur128.c histogram tables (same libm calls as the C library)
     {

@@ -491,35 +491,48 @@ constexpr int kChainStages = 2;    // segment buffers in flight between the prod
 __device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-// k_att_chain: the strictly sequential part.  One CTA of two warps per (chunk, band):
-//   warp 0, the PRODUCER, walks the 256-frame segments of the rms plane (lane = 8 consecutive frames), compacts the
+// k_att_chain: the strictly sequential part.  Two warps per (chunk, band), four chains per CTA:
+//   a PRODUCER warp walks the 256-frame segments of the rms plane (lane = 8 consecutive frames), compacts the
 //     table entries (M, tau, inc, dec) of the flagged frames into a shared-memory queue in time order, padded to a
 //     multiple of 16 with no-op entries, and later scatters the results (attenuation after every flagged frame ->
 //     att_f, attenuation entering every 32-frame group -> ckpt);
-//   warp 1, the CONSUMER, does nothing but the recurrence over those queues: 16 steps per iteration from two
+//   a CONSUMER warp does nothing but the recurrence over those queues: 16 steps per iteration from two
 //     ping-pong register blocks so the shared-memory loads of the next 8 steps are in flight while the current 8
 //     run - 25 cycles per dependent step on B200 (profiles/micro/att_chain_latency3.cu), and segments without
 //     flagged frames cost it one barrier.
 // The two warps are decoupled by kChainStages buffers and named barriers (full[s]: producer arrives / consumer
 // waits; done[s]: consumer arrives / producer waits).
-__global__ void __launch_bounds__(64)
+constexpr int kChainsPerCta = 4;   // consumers = warps 0..3, producers = warps 4..7: one of each per SM sub-partition
+struct ChainSmem {                 // per chain
+    double2 mt[kChainStages][kSeg + 32];     // (M, tau)   (+16 no-op entries, +8 read-ahead slack)
+    double2 id[kChainStages][kSeg + 32];     // (inc, dec)
+    double att[kChainStages][kSeg + 16];     // attenuation after each flagged frame
+    double att_in[kChainStages];             // attenuation entering the segment
+    int total[kChainStages];
+    uint16_t off[kChainStages][32];          // producer bookkeeping for the scatter
+    uint8_t m8[kChainStages][32];
+};
+
+__global__ void __launch_bounds__(kChainsPerCta * 64)
 k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
             const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
-    __shared__ double2 s_mt[kChainStages][kSeg + 32];     // (M, tau)   (+16 no-op entries, +8 read-ahead slack)
-    __shared__ double2 s_id[kChainStages][kSeg + 32];     // (inc, dec)
-    __shared__ double s_att[kChainStages][kSeg + 16];     // attenuation after each flagged frame
-    __shared__ double s_att_in[kChainStages];             // attenuation entering the segment
-    __shared__ int s_total[kChainStages];
-    __shared__ uint8_t s_m8[kChainStages][32];            // producer bookkeeping for the scatter
-    __shared__ uint16_t s_off[kChainStages][32];
-    const int job_i = blockIdx.x;
-    if (job_i >= n_jobs) return;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    // Warp w of a CTA lands on SM sub-partition w % 4.  With 64-thread CTAs every consumer warp sat on sub-partitions
+    // 1 and 3 and, at ~8 chains per SM, four latency-bound recurrences shared one issue port (24 instead of 10
+    // cycles/frame for 1152 chains).  Four chains per CTA put one consumer and one producer on every sub-partition.
+    const int warp = threadIdx.x >> 5;
+    const int chain = warp & (kChainsPerCta - 1);
+    const bool producer = warp >= kChainsPerCta;
+    ChainSmem &sm = reinterpret_cast<ChainSmem *>(s_raw)[chain];
+    auto &s_mt = sm.mt; auto &s_id = sm.id; auto &s_att = sm.att; auto &s_att_in = sm.att_in; auto &s_total = sm.total;
+    auto &s_off = sm.off; auto &s_m8 = sm.m8;
+    const int job_i = blockIdx.x * kChainsPerCta + chain;
+    if (job_i >= n_jobs) return;                          // both warps of that chain leave; barriers are per chain
     const int lane = threadIdx.x & 31;
-    const bool producer = threadIdx.x < 32;
     const ChainJob job = jobs[job_i];
     const int64_t n = job.n;
     const int64_t n_seg = (n + kSeg - 1) / kSeg;
-    constexpr int FULL = 1, DONE = 1 + kChainStages;      // named barrier ids (0 is __syncthreads)
+    const int FULL = chain * 2 * kChainStages, DONE = FULL + kChainStages;   // named barrier ids 0..15, 64 threads each
 
     if (!producer) {
         // ------------------------------------------------------------------ consumer: the recurrence only
@@ -529,7 +542,9 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
             named_sync(FULL + st);
             const int total = s_total[st];
             if (lane == 0) s_att_in[st] = att;
-            if (total) {
+            // one active lane is enough (the warp would only repeat the same scalar work 32 times); it also keeps the
+            // shared-memory traffic of the operand loads at 16 B instead of 32 x 16 B per instruction
+            if (total && lane == 0) {
                 const double2 *__restrict__ qmt = s_mt[st];
                 const double2 *__restrict__ qid = s_id[st];
                 double *__restrict__ qa = s_att[st];
@@ -553,6 +568,7 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
                     }
                 }
             }
+            att = __shfl_sync(kFull, att, 0);
             named_arrive(DONE + st);
         }
         return;
