@@ -253,3 +253,38 @@ def test_host_path_waves_equal_single_wave(torch_cuda):
         b, ib = master(tracks, fs, sets, chunk_seconds=1, n_waves=waves)
         assert all(np.array_equal(x, y) for x, y in zip(a, b)), waves
         assert [i["input_i"] for i in ia] == [i["input_i"] for i in ib]
+
+
+def test_random_settings_sweep(torch_cuda):
+    """Randomised settings over the GUI slider ranges (mastering_gui.py:44-55) and several sample rates, one
+    batch per rate, every track against the oracle."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    rng = np.random.default_rng(2026)
+    worst = 0
+    for fs in (22050, 32000, 44100, 48000, 88200, 96000):
+        tracks, sets = [], []
+        for k in range(6):
+            def pick(lo, hi, zero_p=0.25):
+                return 0.0 if rng.random() < zero_p else float(np.round(rng.uniform(lo, hi), 1))
+            s = dict(bass_boost=pick(-6, 6), mid_cut=pick(0, 6), presence_boost=pick(-6, 6), treble_boost=pick(-6, 6),
+                     width=float(np.round(rng.uniform(0, 2), 2)) if rng.random() < 0.7 else 1.0,
+                     analog_character=0 if (rng.random() < 0.4 or fs < 30000) else int(rng.integers(1, 101)),
+                     lufs=None if rng.random() < 0.15 else float(np.round(rng.uniform(-20, -6), 1)),
+                     multiband=bool(rng.random() < 0.6))
+            for b in ("low", "mid", "high"):
+                s[b + "_thresh"] = float(np.round(rng.uniform(-40, 0), 1))
+                s[b + "_ratio"] = float(np.round(rng.uniform(1, 10), 1))
+            secs = float(rng.uniform(0.45, 1.6))
+            x = synth.track(secs, fs, track_id=100 + k, am_hz=float(rng.uniform(1, 8)), am_db=float(rng.uniform(0, 12)))
+            x = np.clip(x.astype(np.float64) * 10 ** (rng.uniform(-12, 9) / 20), -32768, 32767).astype(np.int16)
+            tracks.append(x); sets.append(s)
+        outs, infos = master(tracks, fs, sets, chunk_seconds=0.5)
+        for x, s, out, info in zip(tracks, sets, outs, infos):
+            ref, rinfo = chain.master(x, fs, s, chunk_seconds=0.5)
+            d = _maxdiff(out, ref)
+            worst = max(worst, d)
+            assert d <= NULL_LSB, (fs, s, d)
+            if s["lufs"] is not None:
+                assert _lufs_close(info["input_i"], rinfo["input_i"]), (fs, s)
+    print("random sweep worst LSB diff", worst)
