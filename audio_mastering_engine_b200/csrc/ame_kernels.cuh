@@ -74,9 +74,10 @@ __device__ __forceinline__ double i16_to_f64(int x) {
 }
 
 // np.clip(x,-1,1) * 32767 -> astype(int16)  (truncate toward zero), float64 flavour
+// (clip first or clamp the truncated product: same integer - the product is monotone in v, +-32767 are exact, and
+// cvt.rzi saturates; the integer clamp avoids two DSETP-based double min/max)
 __device__ __forceinline__ int to_pcm_f64(double v) {
-    v = fmin(fmax(v, -1.0), 1.0);
-    return __double2int_rz(__dmul_rn(v, 32767.0));
+    return min(max(__double2int_rz(__dmul_rn(v, 32767.0)), -32767), 32767);
 }
 __device__ __forceinline__ int to_pcm_f32(float v) {
     v = fminf(fmaxf(v, -1.0f), 1.0f);
@@ -413,6 +414,11 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
     const int look = cj.look;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t i0 = t0 + (int64_t)threadIdx.x * 8;
+    // all loads first (the kernel is bound by memory latency): this thread's 8 frames, the 8 frames `look` earlier,
+    // and its share of the window entering the tile
+    uint32_t w[8], wo[8];
+    load8(bp, i0, 0, n, w);
+    load8(bp, i0 - look, 0, n, wo);
     // window sum entering the tile: frames [t0 - look, t0)
     unsigned long long head = 0;
     for (int64_t j = t0 - look + threadIdx.x; j < t0; j += kWfThreads)
@@ -421,9 +427,6 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
     for (int d = 16; d > 0; d >>= 1) head += __shfl_xor_sync(kFull, head, d);
     if (lane == 0) s_head[wid] = head;
     // D_j = e_j - e_{j-look}; S_i = head + sum_{t0 <= j < i} D_j
-    uint32_t w[8], wo[8];
-    load8(bp, i0, 0, n, w);
-    load8(bp, i0 - look, 0, n, wo);
     long long pre[8];          // exclusive prefix of D inside the thread
     long long run = 0;
 #pragma unroll
@@ -672,6 +675,10 @@ __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fboun
 // the value k_att_chain stored for the last flagged frame at or before it inside its 32-frame group, or the
 // group's entry value; gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)), skipped
 // when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
+// pydub db_to_float(-att) = 10 ** (-att / 20); out of line so the 24 call sites of k_compress_apply share one copy
+// (the fully inlined kernel thrashed the instruction cache: stall_no_instruction 1.7 per issue)
+__device__ __noinline__ double gain_of_att(double att) { return exp10(-att / 20.0); }
+
 __global__ void __launch_bounds__(128)
 k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
                  const int16_t *__restrict__ bands, const uint16_t *__restrict__ rms,
@@ -722,7 +729,7 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_l
             const unsigned below = flags & (0xffffffffu >> (31 - lane));
             const double mine = below ? __ldg(ap + (i - lane) + (31 - __clz(below))) : ce[b][g];
             if (mine != 0.0) {
-                if (mine != c_att) { c_att = mine; c_fac = exp10(-mine / 20.0); }
+                if (mine != c_att) { c_att = mine; c_fac = gain_of_att(mine); }
                 l = mul_floor(l, c_fac);
                 r = mul_floor(r, c_fac);
             }

@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--fs", type=int, default=48000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-waves", type=int, default=16)
-    ap.add_argument("--waves", type=int, default=3, help="plan waves of the device-resident path")
+    ap.add_argument("--waves", type=int, default=2, help="plan waves of the device-resident path")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
