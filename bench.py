@@ -161,9 +161,18 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the communicator is created: send fd 1 to stderr until the
+        # first collective is through, so that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
