@@ -473,15 +473,25 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     int n_waves = o.n_waves > 0 ? o.n_waves : 1;
     n_waves = std::max(1, std::min(n_waves, n_tracks));
     {
+        // With many waves the FIRST wave is a single track: in the host path nothing can be copied back before the
+        // first wave has been copied in and mastered, so a small first wave starts the D2H stream early.
         p->waves.resize(n_waves);
+        const bool small_first = o.host_io && n_waves >= 4 && n_tracks >= 2 * n_waves;
         int t = 0;
         int64_t acc = 0;
+        const int64_t first_frames = small_first ? p->tracks[0].n_frames : 0;
         for (int w = 0; w < n_waves; ++w) {
             Wave &wv = p->waves[w];
             wv.track_lo = t;
-            const int64_t target = sum_frames * (w + 1) / n_waves;
             const int must_leave = n_waves - 1 - w;                 // at least one track for every later wave
-            while (t < n_tracks - must_leave && (t == wv.track_lo || acc + p->tracks[t].n_frames / 2 <= target)) acc += p->tracks[t++].n_frames;
+            if (small_first && w == 0) {
+                acc += p->tracks[t++].n_frames;
+            } else {
+                const int64_t share = small_first ? w : w + 1;
+                const int64_t parts = small_first ? n_waves - 1 : n_waves;
+                const int64_t target = first_frames + (sum_frames - first_frames) * share / parts;
+                while (t < n_tracks - must_leave && (t == wv.track_lo || acc + p->tracks[t].n_frames / 2 <= target)) acc += p->tracks[t++].n_frames;
+            }
             if (w == n_waves - 1) t = n_tracks;
             wv.track_hi = t;
             wv.frame_lo = p->tracks[wv.track_lo].offset_frames;
@@ -502,8 +512,12 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
-    const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128;         // one thread per tile
-    const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128;
+    // Waves run on separate streams, so up to ~4 of them share the machine at any time: a wave's launch gets that
+    // share of the resident threads (sizing every wave to fill the machine alone made 16-wave plans do 2.3x the
+    // filter work in warm-up).
+    const int share = std::min(n_waves, 4);
+    const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128 / share;         // one thread per tile
+    const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128 / share;
     constexpr int64_t kMinTile = 512;
     int64_t split_tile = kMinTile;
     std::vector<double> eq_cost(n_tracks);
@@ -525,7 +539,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         // a tile of sub-blocks costs (tile + warm-up) frames: keep the warm-up below ~15 % when the batch is big
         // enough to still give every SM ~512 threads per launch, else shrink the tile towards one sub-block
         const int64_t want = std::max<int64_t>(1, ((int64_t)max_warm_kw * 6 + min_s100 - 1) / min_s100);
-        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / n_waves / ((int64_t)n_sm * 512));
+        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / n_waves * share / ((int64_t)n_sm * 512));
         p->kw_tile_sb = (int)std::min(want, fill);
     }
 

@@ -5,7 +5,10 @@ import torch
 from audio_mastering_engine_b200 import MasterPlan, synth, EQ_PRESETS
 n_tr, fs, secs = 128, 48000, 180.0
 n = int(secs * fs)
-settings = [synth.c4_settings(k, EQ_PRESETS) for k in range(n_tr)]
+ids = list(range(n_tr))
+if os.environ.get('ORDERED') == '1':
+    mb = [t for t in ids if t % 2 == 1]; nb = [t for t in ids if t % 2 == 0]; ids = nb[:2] + mb + nb[2:]
+settings = [synth.c4_settings(k, EQ_PRESETS) for k in ids]
 dev = torch.device("cuda", 0)
 tracks = synth.torch_track_batch(n_tr, secs, fs, dev)
 h_in = torch.empty((n_tr * n, 2), dtype=torch.int16, pin_memory=True)
