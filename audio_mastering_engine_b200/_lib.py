@@ -40,7 +40,7 @@ class TrackParams(C.Structure):
 class TrackResult(C.Structure):
     _fields_ = [("input_i", C.c_double), ("measured_i_2dp", C.c_double), ("gain", C.c_double),
                 ("rel_threshold", C.c_double), ("n_blocks", C.c_int64), ("normalized", C.c_int32),
-                ("sample_peak", C.c_int32)]
+                ("sample_peak", C.c_int32), ("input_lra", C.c_double), ("input_thresh", C.c_double)]
 
 
 class PlanOptions(C.Structure):

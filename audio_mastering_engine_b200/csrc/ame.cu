@@ -97,6 +97,7 @@ struct ame_plan {
     uint16_t *d_rms = nullptr;
     double *d_ckpt = nullptr, *d_attf = nullptr, *d_energy = nullptr;
     long long *d_hist = nullptr;
+    int *d_hist_st = nullptr;               // short-term (3 s) histogram per track, for loudness range
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
@@ -350,7 +351,7 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     LAUNCH_CHECK(p);
     t_end(p, S_TAIL, s);
     t_begin(p, S_HIST, s);
-    k_block_hist<<<nt, 256, 0, s>>>(p->d_tdev, w.track_lo, p->d_energy, (long long *)d_hist);
+    k_block_hist<<<nt, 256, 0, s>>>(p->d_tdev, w.track_lo, p->d_energy, (long long *)d_hist, p->d_hist_st);
     LAUNCH_CHECK(p);
     t_end(p, S_HIST, s);
     return AME_OK;
@@ -360,7 +361,7 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
     t_begin(p, S_FIN, s);
-    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_peak, p->d_results);
+    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_hist_st, p->d_peak, p->d_results);
     LAUNCH_CHECK(p);
     t_end(p, S_FIN, s);
     if (w.gain_n) {
@@ -403,7 +404,7 @@ void ame_plan_destroy(ame_plan *p) {
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
-                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_peak, p->d_results};
+                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaStream_t s : {p->s_in, p->s_out})
@@ -664,6 +665,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         (rc = dmalloc(p, (void **)&p->d_attf, (size_t)p->mb_frames * 8 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_energy, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
+        (rc = dmalloc(p, (void **)&p->d_hist_st, (size_t)n_tracks * 1000 * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_results, (size_t)n_tracks * sizeof(ame_track_result))))
         return bail(rc);

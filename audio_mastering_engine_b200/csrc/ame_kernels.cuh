@@ -823,12 +823,16 @@ __device__ __forceinline__ int hist_index(double e) {   // ebur128.c find_histog
     return lo;
 }
 
-// k_block_hist: 400 ms blocks every 100 ms -> 1000-bin histogram (absolute gate = bin floor, -70 LUFS)
+// k_block_hist: 400 ms blocks every 100 ms -> 1000-bin histogram (absolute gate = bin floor, -70 LUFS), and the
+// short-term histogram behind loudness range: 3 s windows, the first ending at 3 s, then one per second
+// (ebur128.c: short_term_frame_counter reaches 30 sub-blocks, is reset to 20).
 __global__ void __launch_bounds__(256)
-k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__restrict__ energy, long long *__restrict__ hist) {
+k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__restrict__ energy, long long *__restrict__ hist,
+             int *__restrict__ hist_st) {
     __shared__ unsigned s_hist[1000];
+    __shared__ unsigned s_st[1000];
     const int t = track_lo + blockIdx.x;
-    for (int i = threadIdx.x; i < 1000; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < 1000; i += blockDim.x) { s_hist[i] = 0; s_st[i] = 0; }
     __syncthreads();
     const TrackDev td = tdev[t];
     const double *e = energy + td.sb_offset;
@@ -837,13 +841,23 @@ k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__re
         const double s = (((e[j] + e[j + 1]) + e[j + 2]) + e[j + 3]) / denom;
         if (s >= c_hist_bounds[0]) atomicAdd(&s_hist[hist_index(s)], 1u);
     }
+    const double denom_st = (double)(30 * (int64_t)td.s100);
+    for (int k = threadIdx.x; 10 * k + 29 < td.n_sb; k += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < 30; ++j) s += e[10 * k + j];
+        s /= denom_st;
+        if (s >= c_hist_bounds[0]) atomicAdd(&s_st[hist_index(s)], 1u);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 1000; i += blockDim.x) hist[(int64_t)t * 1000 + i] = (long long)s_hist[i];
+    for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
+        hist[(int64_t)t * 1000 + i] = (long long)s_hist[i];
+        hist_st[(int64_t)t * 1000 + i] = (int)s_st[i];
+    }
 }
 
-// k_finalize: ebur128_gated_loudness + the linear-mode gain of af_loudnorm, one thread per track
+// k_finalize: ebur128_gated_loudness + loudness range + the linear-mode gain of af_loudnorm, one thread per track
 __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_hi,
-                           const long long *__restrict__ hist, const int *__restrict__ peak,
+                           const long long *__restrict__ hist, const int *__restrict__ hist_st, const int *__restrict__ peak,
                            ame_track_result *__restrict__ res) {
     const int t = track_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= track_hi) return;
@@ -851,6 +865,7 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
     ame_track_result r;
     r.input_i = -INFINITY; r.measured_i_2dp = -INFINITY; r.gain = 1.0; r.rel_threshold = 0.0;
     r.n_blocks = 0; r.normalized = 0; r.sample_peak = peak[t];
+    r.input_lra = 0.0; r.input_thresh = -70.0;
     double rel = 0.0; long long count = 0;
     for (int j = 0; j < 1000; ++j) { rel += (double)h[j] * c_hist_energy[j]; count += h[j]; }
     r.n_blocks = count;
@@ -858,6 +873,7 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
         rel /= (double)count;
         rel *= 0.1;                                  // RELATIVE_GATE_FACTOR = 10^(-10/10)
         r.rel_threshold = rel;
+        r.input_thresh = 10.0 * log10(rel) - 0.691;  // ff_ebur128_relative_threshold
         int start;
         if (rel < c_hist_bounds[0]) start = 0;
         else { start = hist_index(rel); if (rel > c_hist_energy[start]) ++start; }
@@ -870,6 +886,30 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
                 r.measured_i_2dp = rint(r.input_i * 100.0) / 100.0;   // the '%.2f' string of pass 1
                 r.gain = pow(10.0, (tracks[t].target_lufs - r.measured_i_2dp) / 20.0);
                 r.normalized = 1;
+            }
+        }
+    }
+    // ff_ebur128_loudness_range: short-term blocks above (mean power - 20 dB), 10th .. 95th percentile
+    {
+        const int *hs = hist_st + (int64_t)t * 1000;
+        long long n = 0; double power = 0.0;
+        for (int j = 0; j < 1000; ++j) { n += hs[j]; power += (double)hs[j] * c_hist_energy[j]; }
+        if (n > 0) {
+            power /= (double)n;
+            const double integ = 0.01 * power;       // MINUS_20DB
+            int idx;
+            if (integ < c_hist_bounds[0]) idx = 0;
+            else { idx = hist_index(integ); if (integ > c_hist_energy[idx]) ++idx; }
+            long long m = 0;
+            for (int j = idx; j < 1000; ++j) m += hs[j];
+            if (m > 0) {
+                const long long p_lo = (long long)((double)(m - 1) * 0.1 + 0.5), p_hi = (long long)((double)(m - 1) * 0.95 + 0.5);
+                long long acc = 0; int j = idx;
+                while (acc <= p_lo) acc += hs[j++];
+                const double l_en = c_hist_energy[j - 1];
+                while (acc <= p_hi) acc += hs[j++];
+                const double h_en = c_hist_energy[j - 1];
+                r.input_lra = (10.0 * log10(h_en) - 0.691) - (10.0 * log10(l_en) - 0.691);
             }
         }
     }

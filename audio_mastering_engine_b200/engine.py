@@ -104,11 +104,22 @@ class MasterPlan:
                 for off, ln, h in zip(self.offsets, self.lengths, self.halos)]
 
     def results(self):
+        """Per-track loudness report: the numbers ffmpeg's loudnorm prints as JSON (audio_mastering_engine.py:229-237),
+        plus whether real ffmpeg would have stayed in LINEAR mode (static gain) - this build always applies the
+        static gain (deviation D3)."""
         out = []
-        for r in self._results:
-            out.append(dict(input_i=r.input_i, measured_i_2dp=r.measured_i_2dp, gain=r.gain,
-                            rel_threshold_energy=r.rel_threshold, n_blocks=int(r.n_blocks),
-                            normalized=bool(r.normalized), sample_peak=int(r.sample_peak)))
+        for r, s in zip(self._results, self.settings):
+            d = dict(input_i=r.input_i, measured_i_2dp=r.measured_i_2dp, gain=r.gain,
+                     rel_threshold_energy=r.rel_threshold, n_blocks=int(r.n_blocks),
+                     normalized=bool(r.normalized), sample_peak=int(r.sample_peak),
+                     input_lra=r.input_lra, input_thresh=r.input_thresh)
+            # native-rate sample peak stands in for ffmpeg's 192 kHz-resampled peak (deviation D4)
+            d["input_tp"] = 20.0 * math.log10(r.sample_peak / 32768.0) if r.sample_peak > 0 else -math.inf
+            if r.normalized:
+                offset = float(s.get("lufs")) - r.measured_i_2dp
+                d["target_offset"] = offset
+                d["linear_mode_ok"] = bool(d["input_tp"] + offset <= -1.5 and r.input_lra <= 11.0)   # TP=-1.5:LRA=11 (:229)
+            out.append(d)
         return out
 
     @property

@@ -119,6 +119,9 @@ class TimeShard:
         if not self.n:
             return self.torch.zeros((0, 2), dtype=self.torch.int16, device=self.dev), None
         info = self.plan.stage_apply_gain(self.d_pre, d_hist, self.d_out, stream)[0]
+        if self.world > 1:                                # short-term (3 s) windows are not stitched across shards
+            info["input_lra"] = None
+            info.pop("linear_mode_ok", None)
         return self.d_out[self.halo:self.halo + self.n], info
 
     def close(self):

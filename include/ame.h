@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AME_ABI_VERSION 2
+#define AME_ABI_VERSION 3
 #define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
@@ -114,6 +114,8 @@ typedef struct {
     int64_t n_blocks;        /* 400 ms blocks above the absolute gate */
     int32_t normalized;      /* 1 iff a gain was applied */
     int32_t sample_peak;     /* max |s16| of the pre-normalisation signal */
+    double input_lra;        /* loudness range, LU (ebur128 short-term histogram, 10th..95th percentile) */
+    double input_thresh;     /* relative gate threshold, LUFS (ffmpeg's input_thresh) */
 } ame_track_result;
 
 typedef struct {

@@ -417,6 +417,53 @@ def gated_loudness_from_histogram(hist):
     return 10.0 * math.log10(gated) - 0.691, rel
 
 
+def short_term_histogram(sub, fs):
+    """ebur128.c LRA mode: 3 s windows (30 sub-blocks), the first ending at 3 s, then one every second."""
+    s100 = samples_in_100ms(fs)
+    hist = np.zeros(1000, dtype=np.int64)
+    k = 0
+    while 10 * k + 29 < len(sub):
+        e = 0.0
+        for j in range(30):
+            e += float(sub[10 * k + j])
+        e /= float(30 * s100)
+        if e >= _BOUNDS[0]:
+            hist[find_histogram_index(e)] += 1
+        k += 1
+    return hist
+
+
+def loudness_range_from_histogram(hist):
+    """ff_ebur128_loudness_range: blocks above (mean power - 20 dB), 10th to 95th percentile, in LU."""
+    hist = np.asarray(hist, dtype=np.int64)
+    n = int(hist.sum())
+    if n == 0:
+        return 0.0
+    power = 0.0
+    for j in range(1000):
+        power += float(hist[j]) * _ENERGIES[j]
+    power /= float(n)
+    integ = math.pow(10.0, -20.0 / 10.0) * power
+    if integ < _BOUNDS[0]:
+        idx = 0
+    else:
+        idx = find_histogram_index(integ)
+        if integ > _ENERGIES[idx]:
+            idx += 1
+    m = int(hist[idx:].sum())
+    if m == 0:
+        return 0.0
+    p_lo, p_hi = int((m - 1) * 0.1 + 0.5), int((m - 1) * 0.95 + 0.5)
+    acc, j = 0, idx
+    while acc <= p_lo:
+        acc += int(hist[j]); j += 1
+    l_en = _ENERGIES[j - 1]
+    while acc <= p_hi:
+        acc += int(hist[j]); j += 1
+    h_en = _ENERGIES[j - 1]
+    return (10.0 * math.log10(h_en) - 0.691) - (10.0 * math.log10(l_en) - 0.691)
+
+
 def integrated_loudness(pcm, fs):
     blocks, _ = gating_block_energies(pcm, fs)
     return gated_loudness_from_histogram(block_histogram(blocks))[0]
@@ -442,6 +489,8 @@ def normalize(pcm, fs, target_lufs, info=None):
     hist = block_histogram(blocks)
     measured, rel = gated_loudness_from_histogram(hist)
     if info is not None:
+        info.update(input_lra=loudness_range_from_histogram(short_term_histogram(sub, fs)),
+                    input_thresh=(10.0 * math.log10(rel) - 0.691) if hist.sum() else -70.0)
         info.update(input_i=measured, hist=hist, n_blocks=int(hist.sum()), rel_threshold_energy=rel,
                     sample_peak=int(np.abs(pcm.astype(np.int32)).max()) if len(pcm) else 0)
     if measured == -math.inf:  # engine.py:238-239 - silent audio, copy through

@@ -127,6 +127,8 @@ def test_master_vs_oracle(torch_cuda, fs, secs, chunk, settings_name):
         assert _lufs_close(info["input_i"], rinfo["input_i"])
         assert info["measured_i_2dp"] == rinfo["measured_i_2dp"]
         assert info["n_blocks"] == rinfo["n_blocks"]
+        assert info["input_lra"] == pytest.approx(rinfo["input_lra"], abs=1e-9)
+        assert info["input_thresh"] == pytest.approx(rinfo["input_thresh"], abs=1e-9) or info["n_blocks"] == 0
         d = _maxdiff(out, ref)
         assert d <= NULL_LSB, (tile, d)
         assert _nz(out, ref) < 5e-3

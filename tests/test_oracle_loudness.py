@@ -76,3 +76,16 @@ def test_static_gain_rounding_and_apply():
     x = np.array([[100, -100], [32767, -32768], [3, -3]], dtype=np.int16)
     y = chain.apply_static_gain(x, 1.5)
     assert y.tolist() == [[150, -150], [32767, -32768], [4, -4]]  # lrint: 4.5 -> 4 (half to even)
+
+
+def test_loudness_range_known_answer():
+    """EBU Tech 3342 style: equal halves at -20 and -30 LUFS => LRA = 10 LU (+-1)."""
+    a = _sine(48000, 20, 1000, -20.0)
+    b = _sine(48000, 20, 1000, -30.0)
+    x = np.concatenate([a, b])
+    _, sub = chain.gating_block_energies(x, 48000)
+    lra = chain.loudness_range_from_histogram(chain.short_term_histogram(sub, 48000))
+    assert abs(lra - 10.0) <= 1.0
+    _, sub = chain.gating_block_energies(a, 48000)
+    assert chain.loudness_range_from_histogram(chain.short_term_histogram(sub, 48000)) < 0.2
+    assert chain.loudness_range_from_histogram(np.zeros(1000, dtype=np.int64)) == 0.0
