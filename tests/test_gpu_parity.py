@@ -290,3 +290,27 @@ def test_random_settings_sweep(torch_cuda):
             if s["lufs"] is not None:
                 assert _lufs_close(info["input_i"], rinfo["input_i"]), (fs, s)
     print("random sweep worst LSB diff", worst)
+
+
+def test_bypass_identity_and_idempotent_normalisation(torch_cuda):
+    """Property checks: with every stage at its neutral setting the path reduces to the
+    reference's lossy int16 -> float -> int16 converter pair; normalising an already normalised track is a no-op
+    within one LSB; ratio 1 compressors pass the bands through; width 1.0 is a bypass, not an M/S round trip."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    fs = 48000
+    x = synth.track(3.0, fs, 21, am_hz=3.0)
+    flat = dict(bass_boost=0.0, mid_cut=0.0, presence_boost=0.0, treble_boost=0.0, analog_character=0, width=1.0,
+                lufs=None, multiband=False)
+    out, info = master(x, fs, flat)
+    assert np.array_equal(out, chain.to_pcm(chain.to_float(x)))          # engine.py:250-257 only
+    assert not info["normalized"] and info["gain"] == 1.0
+    once, i1 = master(x, fs, dict(flat, lufs=-14.0))
+    twice, i2 = master(once, fs, dict(flat, lufs=-14.0))
+    assert abs(i2["input_i"] - (-14.0)) < 0.02
+    assert _maxdiff(chain.to_pcm(chain.to_float(once)), twice) <= 1
+    unity = dict(flat, multiband=True, low_thresh=-30.0, low_ratio=1.0, mid_thresh=-30.0, mid_ratio=1.0,
+                 high_thresh=-30.0, high_ratio=1.0)
+    mb, _ = master(x, fs, unity)
+    lo, mi, hi = chain.band_split(chain.to_pcm(chain.to_float(x)), fs)
+    assert np.array_equal(mb, chain.overlay(chain.overlay(lo, mi), hi))  # ratio 1 => M = 0 => untouched bands
