@@ -78,6 +78,7 @@ struct ame_plan {
     int64_t mb_frames = 0;                // padded
     int64_t n_group_total = 0, n_sb_total = 0;
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
+    int n_sm = 148, chain_warps = 0;      // see chain_threads()
     size_t ws_bytes = 0;
     int64_t launches = 0;
     // device
@@ -317,6 +318,19 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
     return AME_OK;
 }
 
+// k_att_chain_spec or k_att_chain?  The speculative kernel cuts the latency of a chain ~6x (32..256 lanes walk it)
+// but pays an uncoalesced 32-byte table gather and an 8-byte store per flagged frame and lane: ~36 us of machine time
+// per 30 s chain, against a flat ~13 ms for ANY number of chains up to 8 per SM with the queue kernel, which keeps
+// one lane per chain busy and leaves the machine to the other streams (profiles/r01e_summary.md).  So: speculative
+// for small plans, queue kernel for batches.  Returns the threads per chain of the speculative kernel, 0 = queue.
+int chain_threads(const ame_plan *p, int n_chains) {
+    if (p->chain_warps < 0) return 0;
+    if (p->chain_warps > 0) return 32 * p->chain_warps;
+    if (p->all.chain_n > p->n_sm) return 0;
+    const int warps = p->n_sm / (2 * std::max(n_chains, 1));
+    return 32 * std::max(1, std::min(warps, kChainMaxThreads / 32));
+}
+
 int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_pre, cudaStream_t s) {
     if (!w.chain_n) return AME_OK;
     t_begin(p, S_FLAG, s);
@@ -324,8 +338,11 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
-    k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
-        p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
+    if (const int ct = chain_threads(p, w.chain_n))
+        k_att_chain_spec<<<w.chain_n, ct, 0, s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
+    else
+        k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
+            p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);
     t_begin(p, S_APPLY, s);
@@ -511,6 +528,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     }
     int n_sm = 148, occ_eq = 2, occ_split = 3;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    p->n_sm = n_sm;
+    p->chain_warps = std::max(-1, std::min(o.chain_warps, kChainMaxThreads / 32));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
     // Waves run on separate streams, so up to ~4 of them share the machine at any time: a wave's launch gets that

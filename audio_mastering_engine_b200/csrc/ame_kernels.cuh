@@ -664,6 +664,133 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
     for (int64_t seg = (n_seg > kChainStages ? n_seg - kChainStages : 0); seg < n_seg; ++seg) flush(seg);
 }
 
+// k_att_chain_spec: the recurrence, made parallel in time by SPECULATION AND REPAIR - exact, not approximate.
+// One CTA per (chunk, band); its S = blockDim.x threads cut the chunk into S contiguous segments and every lane
+// walks its own segment (the lanes of a warp run in lockstep, so a step of the 25-cycle dependent chain advances
+// 32 segments at once):
+//   pass 1   every lane starts from attenuation 0 (lane 0 really does - the reference resets it per chunk);
+//   repair   lane t takes the end value lane t-1 produced in the previous pass.  If that differs from the start it
+//            used, it walks its segment again carrying BOTH attenuations (old start, new start - two independent
+//            chains in one thread, no extra latency) and stops at the first frame where they are bit-equal: from
+//            there on the trajectory it stored before is the right one, and so is its old end value.  A lane that
+//            never meets publishes a new end value;
+//   until no lane's start changed.  By induction every lane has then been walked from the true end of its
+//   predecessor, i.e. the stored values are those of the sequential loop.
+// Trajectories meet whenever both clamp to the same max_attenuation (att in [tau, M] -> M), which the compressor
+// does all the time while it tracks the level: on the bench tracks 0.3k-20k frames after a segment start (two or
+// three passes).  A signal that never clamps degrades to one segment per pass, the sequential cost.
+// Unflagged frames carry rms 0 and table entry 0 (M = inc = dec = tau = 0) is a no-op, so the walk needs no branch
+// per frame; 8-frame blocks without any flagged frame are skipped.
+// Emits the attenuation after every flagged frame (att_f, sparse) and entering every 32-frame group (ckpt).
+constexpr int kChainMaxThreads = 256;
+constexpr int kWalkBlock = 16;     // frames per walker iteration = one 32-byte rms load
+
+struct ChainCtx {
+    const uint16_t *rp;        // rms plane of this chain
+    const AttEntry *tbl;
+    double *af, *ck;
+    int64_t n;
+    bool vec;                  // rp is 32-byte aligned
+};
+
+struct RmsBlock { uint32_t w[kWalkBlock / 2]; };
+
+__device__ __forceinline__ RmsBlock chain_load_rms(const ChainCtx &c, int64_t i) {   // rms of frames i..i+15, 0 past the end
+    RmsBlock q;
+#pragma unroll
+    for (int k = 0; k < kWalkBlock / 2; ++k) q.w[k] = 0;
+    if (i + kWalkBlock <= c.n && c.vec) {
+        // volatile: must stay under the alignment test (a plain asm counts as pure and may be executed speculatively)
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(q.w[0]), "=r"(q.w[1]), "=r"(q.w[2]), "=r"(q.w[3]), "=r"(q.w[4]), "=r"(q.w[5]), "=r"(q.w[6]), "=r"(q.w[7])
+                     : "l"(c.rp + i));
+    } else if (i < c.n) {
+#pragma unroll
+        for (int k = 0; k < kWalkBlock; ++k)
+            if (i + k < c.n) q.w[k >> 1] |= (uint32_t)__ldg(c.rp + i + k) << ((k & 1) * 16);
+    }
+    return q;
+}
+
+// table entries of the 8 frames of half h of a block: one 32-byte load per flagged frame, the no-op entry otherwise.
+// (plain asm, not volatile: the table is constant and tbl + r is always a valid aligned entry, so the compiler may
+// schedule - or speculate - the loads as it likes)
+__device__ __forceinline__ void chain_entries(AttEntry *e, const AttEntry *tbl, const RmsBlock &q, int h) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned r = (q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu;
+        e[k] = AttEntry{0.0, 0.0, 0.0, 0.0};
+        if (r) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e[k].m), "=d"(e[k].inc), "=d"(e[k].dec), "=d"(e[k].tau) : "l"(tbl + r));
+    }
+}
+
+// 8 steps of the recurrence over frames i..i+7 (half h of block q); true when DUAL and a == b afterwards
+template <bool DUAL>
+__device__ __forceinline__ bool chain_step8(const ChainCtx &c, const RmsBlock &q, int h, const AttEntry *e, int64_t i, double &a, double &b) {
+    if ((q.w[4 * h] | q.w[4 * h + 1] | q.w[4 * h + 2] | q.w[4 * h + 3]) == 0) return false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        b = att_update(b, e[k].m, e[k].inc, e[k].dec, e[k].tau);
+        if (DUAL) a = att_update(a, e[k].m, e[k].inc, e[k].dec, e[k].tau);
+        if ((q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu) c.af[i + k] = b;
+    }
+    return DUAL && __double_as_longlong(a) == __double_as_longlong(b);
+}
+
+// Walk frames [b0, b1) (b0 a multiple of 32) from attenuation b; with DUAL also from a, returning true at the first
+// 8-frame group after which the two are bit-equal.  b holds the attenuation reached.  The rms words run two blocks
+// ahead of the recurrence and the table entries one half block ahead (two register blocks, as many loads in flight
+// as the 8 dependent steps they hide behind).
+template <bool DUAL>
+__device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_t b1, double a, double &b) {
+    if (b0 >= b1) return false;
+    RmsBlock cur = chain_load_rms(c, b0), nxt = chain_load_rms(c, b0 + kWalkBlock);
+    AttEntry ea[8], eb[8];
+    chain_entries(ea, c.tbl, cur, 0);
+    for (int64_t i = b0; i < b1; i += kWalkBlock) {
+        const RmsBlock nn = chain_load_rms(c, i + 2 * kWalkBlock);
+        chain_entries(eb, c.tbl, cur, 1);
+        if ((i & 31) == 0) c.ck[i >> 5] = b;
+        if (chain_step8<DUAL>(c, cur, 0, ea, i, a, b)) return true;
+        chain_entries(ea, c.tbl, nxt, 0);
+        if (chain_step8<DUAL>(c, cur, 1, eb, i + 8, a, b)) return true;
+        cur = nxt; nxt = nn;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kChainMaxThreads)
+k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
+                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
+    __shared__ double s_end[kChainMaxThreads];
+    const ChainJob job = jobs[blockIdx.x];
+    const int S = blockDim.x, t = threadIdx.x;
+    ChainCtx c;
+    c.rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
+    c.tbl = tables + (size_t)job.table * 32769;
+    c.af = att_f + (int64_t)job.band * mb_frames + job.mb_begin;
+    c.ck = ckpt + job.ck_begin;
+    c.n = job.n;
+    c.vec = (reinterpret_cast<uintptr_t>(c.rp) & 31) == 0;
+    // whole 32-frame groups per segment: a checkpoint and a 32-byte rms load never straddle two lanes
+    const int64_t seg = (((c.n + S - 1) / S) + 31) & ~(int64_t)31;
+    const int64_t b0 = min(c.n, (int64_t)t * seg), b1 = min(c.n, b0 + seg);
+    double start = 0.0, end = 0.0;
+    chain_walk<false>(c, b0, b1, 0.0, end);
+    for (;;) {
+        s_end[t] = end;
+        __syncthreads();
+        const double from = t ? s_end[t - 1] : 0.0;
+        const bool redo = __double_as_longlong(from) != __double_as_longlong(start);
+        if (!__syncthreads_or(redo)) break;            // also orders the reads of s_end before the next round's writes
+        if (redo) {
+            double b = from;
+            if (!chain_walk<true>(c, b0, b1, start, b)) end = b;
+            start = from;
+        }
+    }
+}
+
 __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
     double v = __dmul_rn((double)x, f);
     if (v > 32767.0) v = 32767.0;

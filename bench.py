@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--fs", type=int, default=48000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-waves", type=int, default=32)
+    ap.add_argument("--chain-warps", type=int, default=0, help="ame_plan_options.chain_warps (0 = auto, -1 = queue kernel)")
     ap.add_argument("--waves", type=int, default=6, help="plan waves of the device-resident path")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,7 +191,7 @@ def run_b200(args, rank, world, local_rank):
     nb = [t for t in ids if not synth.c4_settings(t, EQ_PRESETS)["multiband"]]
     ids = nb[:2] + mb + nb[2:]
     settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
-    plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves)
+    plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves, chain_warps=args.chain_warps)
     assert plan.total_frames == n_tr * ((n + 7) // 8 * 8)
     tracks = synth.torch_track_batch(n_tr, secs, fs, dev, first_track_id=first)        # [n_tr, n, 2] int16
     d_in = torch.zeros((plan.total_frames, 2), dtype=torch.int16, device=dev)
@@ -229,7 +230,7 @@ def run_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         # the host API on its own plan: same batch, split into waves so copies and kernels overlap
-        hplan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, host_io=True, n_waves=args.e2e_waves)
+        hplan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, host_io=True, n_waves=args.e2e_waves, chain_warps=args.chain_warps)
         h_in = torch.empty((plan.total_frames, 2), dtype=torch.int16, pin_memory=True)
         h_out = torch.empty_like(h_in, pin_memory=True)
         h_in.copy_(d_in)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AME_ABI_VERSION 3
+#define AME_ABI_VERSION 4
 #define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
@@ -128,6 +128,8 @@ typedef struct {
                                     of one wave overlaps the bulk kernels of the others, and ame_master_host also
                                     overlaps the H2D copy of wave w+1 and the D2H copy of wave w-1 with the kernels of
                                     wave w.  Tiles shrink with the wave, so more waves = more filter warm-up work */
+    int32_t chain_warps;         /* compressor recurrence: 0 = choose per launch; 1..8 = k_att_chain_spec with that many warps
+                                    (x32 speculative time segments) per chain; -1 = k_att_chain (one lane per chain) */
 } ame_plan_options;
 
 typedef struct ame_plan ame_plan;

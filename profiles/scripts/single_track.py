@@ -4,10 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np, torch
 from audio_mastering_engine_b200 import MasterPlan, synth
 cases = {"c1": (44100, 30.0, synth.c1_settings(), None), "c2": (48000, 180.0, synth.c2_settings(), 2.0)}
+cw = int(os.environ.get("AME_CHAIN_WARPS", "0"))
 for name in sys.argv[1:] or ["c1", "c2"]:
     fs, secs, s, am = cases[name]
     x = synth.track(secs, fs, 0, am_hz=am)
-    plan = MasterPlan([len(x)], fs, s, host_io=True)
+    plan = MasterPlan([len(x)], fs, s, host_io=True, chain_warps=cw)
     h_in = torch.from_numpy(plan.pack([x])).pin_memory(); h_out = torch.empty_like(h_in).pin_memory()
     d_in = h_in.cuda(); d_out = torch.empty_like(d_in)
     for _ in range(3): plan.master_device(d_in, d_out, fetch_results=False)

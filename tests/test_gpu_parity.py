@@ -314,3 +314,34 @@ def test_bypass_identity_and_idempotent_normalisation(torch_cuda):
     mb, _ = master(x, fs, unity)
     lo, mi, hi = chain.band_split(chain.to_pcm(chain.to_float(x)), fs)
     assert np.array_equal(mb, chain.overlay(chain.overlay(lo, mi), hi))  # ratio 1 => M = 0 => untouched bands
+
+
+def test_compressor_kernels_agree(torch_cuda):
+    """The attenuation recurrence has two kernels: k_att_chain (one lane per chain, queue of flagged frames) and
+    k_att_chain_spec (32..256 speculative time segments per chain, repaired until exact).  Same bytes from both, for
+    every segment count, on ragged lengths and on signals built to defeat the speculation: a loud burst followed by a
+    bed that stays just above threshold (the attenuation never clamps again, so every segment has to be re-walked)."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    fs = 48000
+    rng = np.random.default_rng(7)
+    n = 6 * fs + 1237
+    t = np.arange(n) / fs
+    bed = 0.02 * np.sin(2 * np.pi * 440.0 * t) + 0.002 * rng.standard_normal(n)
+    burst = np.where(t < 0.2, 0.9 * np.sin(2 * np.pi * 330.0 * t), 0.0)
+    held = np.stack([bed + burst, bed - burst], axis=1)
+    held = np.clip(held * 32767, -32767, 32767).astype(np.int16)
+    cases = [
+        (synth.track(5.3, fs, track_id=11, am_hz=2.0)[:250003], synth.c2_settings(), 2.0),
+        (synth.stress_track(8.0, fs, track_id=5), dict(synth.c2_settings(), low_thresh=-40.0, mid_thresh=-40.0, high_thresh=-40.0), 30),
+        (held, dict(synth.c2_settings(), low_thresh=-36.0, low_ratio=8.0, mid_thresh=-36.0, mid_ratio=8.0), 30),
+        (synth.track(0.02, fs, track_id=2)[:701], synth.c2_settings(), 30),           # shorter than 32 * 32 frames
+    ]
+    for x, s, chunk in cases:
+        base, binfo = master(x, fs, s, chunk_seconds=chunk, chain_warps=-1)
+        ref, _ = chain.master(x, fs, s, chunk_seconds=chunk)
+        assert _maxdiff(base, ref) <= NULL_LSB
+        for cw in (1, 3, 8):
+            out, info = master(x, fs, s, chunk_seconds=chunk, chain_warps=cw)
+            assert np.array_equal(out, base), cw
+            assert info["input_i"] == binfo["input_i"]
