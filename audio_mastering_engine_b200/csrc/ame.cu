@@ -97,6 +97,7 @@ struct ame_plan {
     int16_t *d_pre = nullptr, *d_bands = nullptr, *d_in = nullptr, *d_out = nullptr;
     uint16_t *d_rms = nullptr;
     double *d_ckpt = nullptr, *d_attf = nullptr, *d_energy = nullptr;
+    int *d_chain_stuck = nullptr;          // per chain: k_att_chain_spec gave up, k_att_chain redoes it
     long long *d_hist = nullptr;
     int *d_hist_st = nullptr;               // short-term (3 s) histogram per track, for loudness range
     int *d_peak = nullptr;
@@ -109,6 +110,8 @@ struct ame_plan {
     int t_step = -1, t_wave = 0;
     std::vector<cudaEvent_t> t_ev;        // [kMaxTimedSteps][kMaxTimedWaves][AME_N_KERNELS][2]
     std::vector<char> t_used;             // [kMaxTimedSteps][kMaxTimedWaves][AME_N_KERNELS]
+    std::vector<cudaEvent_t> tl_ev;       // host-path timeline of the last timed ame_master_host: start, then per wave
+    int tl_waves = 0;                     //   {H2D done, first kernel may start, kernels done, D2H done}
 };
 
 namespace {
@@ -328,7 +331,7 @@ int chain_threads(const ame_plan *p, int n_chains) {
     if (p->chain_warps > 0) return 32 * p->chain_warps;
     if (p->all.chain_n > p->n_sm) return 0;
     const int warps = p->n_sm / (2 * std::max(n_chains, 1));
-    return 32 * std::max(1, std::min(warps, kChainMaxThreads / 32));
+    return 32 * std::max(2, std::min(warps, kChainMaxThreads / 32));   // >= 2 warps: a chain that will not settle is redone in place
 }
 
 int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_pre, cudaStream_t s) {
@@ -338,11 +341,16 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
-    if (const int ct = chain_threads(p, w.chain_n))
-        k_att_chain_spec<<<w.chain_n, ct, 0, s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
-    else
-        k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
-            p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames);
+    const int ct = chain_threads(p, w.chain_n);
+    if (ct) {
+        k_att_chain_spec<<<w.chain_n, ct, ct >= 64 ? sizeof(ChainSmem) : 0, s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames,
+                                                  p->d_chain_stuck + w.chain_lo);
+        LAUNCH_CHECK(p);
+    }
+    // the queue kernel: every chain, or (after the speculative kernel) only those it flagged - a CTA without one exits at once
+    k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
+        p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames,
+        ct ? p->d_chain_stuck + w.chain_lo : nullptr);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);
     t_begin(p, S_APPLY, s);
@@ -421,7 +429,8 @@ void ame_plan_destroy(ame_plan *p) {
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
-                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results};
+                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results,
+                    p->d_chain_stuck};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaStream_t s : {p->s_in, p->s_out})
@@ -430,6 +439,7 @@ void ame_plan_destroy(ame_plan *p) {
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_run) cudaEventDestroy(e);
     for (cudaEvent_t e : p->t_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->tl_ev) cudaEventDestroy(e);
     delete p;
 }
 
@@ -681,6 +691,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     if ((rc = dmalloc(p, (void **)&p->d_pre, fb)) || (rc = dmalloc(p, (void **)&p->d_bands, (size_t)p->mb_frames * 4 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_rms, (size_t)p->mb_frames * 2 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_ckpt, (size_t)p->n_group_total * 8)) ||
+        (rc = dmalloc(p, (void **)&p->d_chain_stuck, chain_jobs.size() * sizeof(int))) ||
         (rc = dmalloc(p, (void **)&p->d_attf, (size_t)p->mb_frames * 8 * 3)) ||
         (rc = dmalloc(p, (void **)&p->d_energy, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
@@ -795,6 +806,16 @@ int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n
     return AME_OK;
 }
 
+int ame_plan_wave_timeline(ame_plan *p, float *ms, int max_waves) {
+    if (!p || !ms) return fail(AME_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    const int n = std::min(p->tl_waves, max_waves);
+    for (int w = 0; w < n; ++w)
+        for (int k = 0; k < 4; ++k) CU(cudaEventElapsedTime(&ms[4 * w + k], p->tl_ev[0], p->tl_ev[1 + 4 * w + k]));
+    return n;
+}
+
 // ---- stage entry points (one launch over the whole batch) ------------------------------------------
 int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream) {
     if (!p || !d_in || !d_pre) return fail(AME_E_INVALID, "NULL argument");
@@ -900,23 +921,37 @@ int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_
     p->launches = 0;
     if (p->timing) ++p->t_step;
     const int nw = (int)p->waves.size();
+    const bool tl = p->timing;
+    if (tl) {
+        while ((int)p->tl_ev.size() < 1 + 4 * nw) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            p->tl_ev.push_back(e);
+        }
+        p->tl_waves = nw;
+        CU(cudaEventRecord(p->tl_ev[0], p->s_in));
+    }
     for (int w = 0; w < nw; ++w) {
         const Wave &wv = p->waves[w];
         const size_t off = (size_t)wv.frame_lo * 4, bytes = (size_t)(wv.frame_hi - wv.frame_lo) * 4;
         CU(cudaMemcpyAsync((char *)p->d_in + off, (const char *)h_in + off, bytes, cudaMemcpyHostToDevice, p->s_in));
         CU(cudaEventRecord(p->ev_in[w], p->s_in));
+        if (tl) CU(cudaEventRecord(p->tl_ev[1 + 4 * w], p->s_in));
     }
     for (int w = 0; w < nw; ++w) {
         CU(cudaStreamWaitEvent(p->s_run[w], p->ev_in[w], 0));
+        if (tl) CU(cudaEventRecord(p->tl_ev[2 + 4 * w], p->s_run[w]));
         p->t_wave = w;
         if ((rc = run_chain_of_stages(p, p->waves[w], p->d_in, p->d_out, p->s_run[w]))) return rc;
         CU(cudaEventRecord(p->ev_run[w], p->s_run[w]));
+        if (tl) CU(cudaEventRecord(p->tl_ev[3 + 4 * w], p->s_run[w]));
     }
     for (int w = 0; w < nw; ++w) {
         const Wave &wv = p->waves[w];
         const size_t off = (size_t)wv.frame_lo * 4, bytes = (size_t)(wv.frame_hi - wv.frame_lo) * 4;
         CU(cudaStreamWaitEvent(p->s_out, p->ev_run[w], 0));
         CU(cudaMemcpyAsync((char *)h_out + off, (const char *)p->d_out + off, bytes, cudaMemcpyDeviceToHost, p->s_out));
+        if (tl) CU(cudaEventRecord(p->tl_ev[4 + 4 * w], p->s_out));
     }
     if (results)
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, p->s_out));

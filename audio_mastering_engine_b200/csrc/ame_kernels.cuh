@@ -516,26 +516,15 @@ struct ChainSmem {                 // per chain
     uint8_t m8[kChainStages][32];
 };
 
-__global__ void __launch_bounds__(kChainsPerCta * 64)
-k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
-            const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    // Warp w of a CTA lands on SM sub-partition w % 4.  With 64-thread CTAs every consumer warp sat on sub-partitions
-    // 1 and 3 and, at ~8 chains per SM, four latency-bound recurrences shared one issue port (24 instead of 10
-    // cycles/frame for 1152 chains).  Four chains per CTA put one consumer and one producer on every sub-partition.
-    const int warp = threadIdx.x >> 5;
-    const int chain = warp & (kChainsPerCta - 1);
-    const bool producer = warp >= kChainsPerCta;
-    ChainSmem &sm = reinterpret_cast<ChainSmem *>(s_raw)[chain];
+// One chain on two warps (consumer: producer == false).  `sm` is that pair's queue, bar_base its first named barrier.
+__device__ __forceinline__ void chain_queue_run(const ChainJob &job, ChainSmem &sm, bool producer, int lane, int bar_base,
+                                                const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
+                                                double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
     auto &s_mt = sm.mt; auto &s_id = sm.id; auto &s_att = sm.att; auto &s_att_in = sm.att_in; auto &s_total = sm.total;
     auto &s_off = sm.off; auto &s_m8 = sm.m8;
-    const int job_i = blockIdx.x * kChainsPerCta + chain;
-    if (job_i >= n_jobs) return;                          // both warps of that chain leave; barriers are per chain
-    const int lane = threadIdx.x & 31;
-    const ChainJob job = jobs[job_i];
     const int64_t n = job.n;
     const int64_t n_seg = (n + kSeg - 1) / kSeg;
-    const int FULL = chain * 2 * kChainStages, DONE = FULL + kChainStages;   // named barrier ids 0..15, 64 threads each
+    const int FULL = bar_base, DONE = FULL + kChainStages;   // 2 * kChainStages named barriers of 64 threads
 
     if (!producer) {
         // ------------------------------------------------------------------ consumer: the recurrence only
@@ -664,6 +653,22 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
     for (int64_t seg = (n_seg > kChainStages ? n_seg - kChainStages : 0); seg < n_seg; ++seg) flush(seg);
 }
 
+__global__ void __launch_bounds__(kChainsPerCta * 64)
+k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
+            const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames,
+            const int *__restrict__ only) {      // only != NULL: just the chains k_att_chain_spec left to this kernel
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    // Warp w of a CTA lands on SM sub-partition w % 4.  With 64-thread CTAs every consumer warp sat on sub-partitions
+    // 1 and 3 and, at ~8 chains per SM, four latency-bound recurrences shared one issue port (24 instead of 10
+    // cycles/frame for 1152 chains).  Four chains per CTA put one consumer and one producer on every sub-partition.
+    const int warp = threadIdx.x >> 5;
+    const int chain = warp & (kChainsPerCta - 1);
+    const int job_i = blockIdx.x * kChainsPerCta + chain;
+    if (job_i >= n_jobs || (only && !only[job_i])) return;   // both warps of that chain leave; barriers are per chain
+    chain_queue_run(jobs[job_i], reinterpret_cast<ChainSmem *>(s_raw)[chain], warp >= kChainsPerCta, threadIdx.x & 31,
+                    chain * 2 * kChainStages, rms, tables, ckpt, att_f, mb_frames);
+}
+
 // k_att_chain_spec: the recurrence, made parallel in time by SPECULATION AND REPAIR - exact, not approximate.
 // One CTA per (chunk, band); its S = blockDim.x threads cut the chunk into S contiguous segments and every lane
 // walks its own segment (the lanes of a warp run in lockstep, so a step of the 25-cycle dependent chain advances
@@ -675,10 +680,11 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
 //            there on the trajectory it stored before is the right one, and so is its old end value.  A lane that
 //            never meets publishes a new end value;
 //   until no lane's start changed.  By induction every lane has then been walked from the true end of its
-//   predecessor, i.e. the stored values are those of the sequential loop.
+//   predecessor, i.e. the stored values are those of the sequential loop.  A chain that does not settle within its
+//   repair budget is flagged in gave_up[] and recomputed by k_att_chain (launched right after, filtered by the flags).
 // Trajectories meet whenever both clamp to the same max_attenuation (att in [tau, M] -> M), which the compressor
 // does all the time while it tracks the level: on the bench tracks 0.3k-20k frames after a segment start (two or
-// three passes).  A signal that never clamps degrades to one segment per pass, the sequential cost.
+// three passes).  A signal that never clamps would degrade to one segment per pass; the budget below cuts that off.
 // Unflagged frames carry rms 0 and table entry 0 (M = inc = dec = tau = 0) is a no-op, so the walk needs no branch
 // per frame; 8-frame blocks without any flagged frame are skipped.
 // Emits the attenuation after every flagged frame (att_f, sparse) and entering every 32-frame group (ckpt).
@@ -712,6 +718,10 @@ __device__ __forceinline__ RmsBlock chain_load_rms(const ChainCtx &c, int64_t i)
     return q;
 }
 
+__device__ __forceinline__ bool chain_any(const RmsBlock &q, int h) {     // a flagged frame in half h of the block?
+    return (q.w[4 * h] | q.w[4 * h + 1] | q.w[4 * h + 2] | q.w[4 * h + 3]) != 0;
+}
+
 // table entries of the 8 frames of half h of a block: one 32-byte load per flagged frame, the no-op entry otherwise.
 // (plain asm, not volatile: the table is constant and tbl + r is always a valid aligned entry, so the compiler may
 // schedule - or speculate - the loads as it likes)
@@ -724,15 +734,23 @@ __device__ __forceinline__ void chain_entries(AttEntry *e, const AttEntry *tbl, 
     }
 }
 
-// 8 steps of the recurrence over frames i..i+7 (half h of block q); true when DUAL and a == b afterwards
+struct SegStat { double max_m, sum_dec; int n_flag, n_grp; };   // of a segment: largest max_attenuation, total release if always above
+                                                                // it, flagged frames, 8-frame groups holding one
+
+// 8 steps of the recurrence over frames i..i+7 (half h of block q); true when DUAL and a == b afterwards.
+// The first (single) walk also gathers the segment statistics.
 template <bool DUAL>
-__device__ __forceinline__ bool chain_step8(const ChainCtx &c, const RmsBlock &q, int h, const AttEntry *e, int64_t i, double &a, double &b) {
-    if ((q.w[4 * h] | q.w[4 * h + 1] | q.w[4 * h + 2] | q.w[4 * h + 3]) == 0) return false;
+__device__ __forceinline__ bool chain_step8(const ChainCtx &c, const RmsBlock &q, int h, const AttEntry *e, int64_t i, double &a, double &b,
+                                            SegStat &st) {
+    if (!chain_any(q, h)) return false;
+    if (!DUAL) ++st.n_grp;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         b = att_update(b, e[k].m, e[k].inc, e[k].dec, e[k].tau);
         if (DUAL) a = att_update(a, e[k].m, e[k].inc, e[k].dec, e[k].tau);
-        if ((q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu) c.af[i + k] = b;
+        const bool flagged = ((q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu) != 0;
+        if (!DUAL) { st.max_m = fmax(st.max_m, e[k].m); st.sum_dec += e[k].dec; st.n_flag += flagged; }
+        if (flagged) c.af[i + k] = b;
     }
     return DUAL && __double_as_longlong(a) == __double_as_longlong(b);
 }
@@ -742,18 +760,23 @@ __device__ __forceinline__ bool chain_step8(const ChainCtx &c, const RmsBlock &q
 // ahead of the recurrence and the table entries one half block ahead (two register blocks, as many loads in flight
 // as the 8 dependent steps they hide behind).
 template <bool DUAL>
-__device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_t b1, double a, double &b) {
+__device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_t b1, double a, double &b, SegStat &st) {
     if (b0 >= b1) return false;
     RmsBlock cur = chain_load_rms(c, b0), nxt = chain_load_rms(c, b0 + kWalkBlock);
     AttEntry ea[8], eb[8];
     chain_entries(ea, c.tbl, cur, 0);
     for (int64_t i = b0; i < b1; i += kWalkBlock) {
         const RmsBlock nn = chain_load_rms(c, i + 2 * kWalkBlock);
-        chain_entries(eb, c.tbl, cur, 1);
         if ((i & 31) == 0) c.ck[i >> 5] = b;
-        if (chain_step8<DUAL>(c, cur, 0, ea, i, a, b)) return true;
+        if (!chain_any(cur, 0) && !chain_any(cur, 1)) {      // 16 silent frames: a dozen instructions instead of ~150
+            if (chain_any(nxt, 0)) chain_entries(ea, c.tbl, nxt, 0);
+            cur = nxt; nxt = nn;
+            continue;
+        }
+        chain_entries(eb, c.tbl, cur, 1);
+        if (chain_step8<DUAL>(c, cur, 0, ea, i, a, b, st)) return true;
         chain_entries(ea, c.tbl, nxt, 0);
-        if (chain_step8<DUAL>(c, cur, 1, eb, i + 8, a, b)) return true;
+        if (chain_step8<DUAL>(c, cur, 1, eb, i + 8, a, b, st)) return true;
         cur = nxt; nxt = nn;
     }
     return false;
@@ -761,8 +784,10 @@ __device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_
 
 __global__ void __launch_bounds__(kChainMaxThreads)
 k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
-                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
-    __shared__ double s_end[kChainMaxThreads];
+                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames, int *__restrict__ gave_up) {
+    __shared__ double s_end[kChainMaxThreads], s_max_m[kChainMaxThreads], s_dec[kChainMaxThreads];
+    __shared__ int s_nflag[kChainMaxThreads], s_ngrp[kChainMaxThreads], s_stuck, s_budget;
+    __shared__ short s_prev[kChainMaxThreads];
     const ChainJob job = jobs[blockIdx.x];
     const int S = blockDim.x, t = threadIdx.x;
     ChainCtx c;
@@ -776,18 +801,72 @@ k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__
     const int64_t seg = (((c.n + S - 1) / S) + 31) & ~(int64_t)31;
     const int64_t b0 = min(c.n, (int64_t)t * seg), b1 = min(c.n, b0 + seg);
     double start = 0.0, end = 0.0;
-    chain_walk<false>(c, b0, b1, 0.0, end);
-    for (;;) {
+    SegStat st{0.0, 0.0, 0, 0};
+    chain_walk<false>(c, b0, b1, 0.0, end, st);
+    // What the first walk tells, before any repair is paid for (thread 0, S <= 256 segments):
+    // * budget.  Measured on B200 (profiles/r01e_summary.md): a repair pass costs a lone warp ~120 cycles per frame of
+    //   every 8-frame group that holds a flagged frame (the walk skips the others; the slowest lane carries ~1.3x the
+    //   mean) plus ~5 per frame of the segment for scanning; the queue kernel, which compacts the flagged frames, 25 cycles per
+    //   flagged frame plus ~4 per frame.  Speculation may cost 80 % of what the queue kernel needs for the chain: a
+    //   band at 12 % flagged frames spread over every group is cheap for the queue and dear to repair, one at 40 %
+    //   in bursts the other way round.
+    // * forecast.  Follow a lower bound of the TRUE attenuation through the segments: where it enters a segment above
+    //   everything that segment can ask for, even after all the release it could get there, the true trajectory never
+    //   clamps in it, cannot meet the speculation, and hands the problem to the next lane.  A run of such segments
+    //   costs one repair pass each (one loud passage, then a bed just over threshold: the reference releases by
+    //   M / release_frames per frame, i.e. hardly at all); a run far longer than the budget is a chain for k_att_chain.
+    // Both only decide WHO computes the chain; what is stored is decided by the bit-equality test alone.
+    s_end[t] = end; s_max_m[t] = st.max_m; s_dec[t] = st.sum_dec; s_nflag[t] = st.n_flag; s_ngrp[t] = st.n_grp;
+    __syncthreads();
+    if (t == 0) {
+        double lb = s_end[0];
+        int run = 0, longest = 0;
+        long long flagged = s_nflag[0], groups = s_ngrp[0];
+        for (int u = 1; u < S; ++u) {
+            flagged += s_nflag[u];
+            groups += s_ngrp[u];
+            const double lo = lb - 1.000001 * s_dec[u];
+            if (lb > 0.0 && lo > s_max_m[u]) { lb = lo; run += s_nflag[u] != 0; longest = max(longest, run); }   // silent segments re-walk for free
+            else { lb = s_end[u]; run = 0; }
+        }
+        const long long budget = 4 * (25 * flagged + 4 * c.n) / (5 * (1250 * groups / S + 5 * seg)) - 1;
+        s_budget = (int)max(2LL, min(budget, (long long)S));
+        s_stuck = longest + 2 > s_budget;      // a run of L such segments needs about L + 2 repairs
+    }
+    __syncthreads();
+    // a segment without a flagged frame hands its start on unchanged: lane t takes the end of the last lane before it
+    // that has one (else a sparse band would pay a pass per silent segment just to pass a number along).  Silent
+    // lanes still re-walk when their start changes - a skip per 16 frames - to refresh their checkpoints.
+    {
+        int u = t - 1;
+        while (u >= 0 && s_nflag[u] == 0) --u;
+        s_prev[t] = (short)u;
+    }
+    const int max_repairs = s_budget;
+    int repairs = 0, stuck = s_stuck;
+    while (!stuck) {
         s_end[t] = end;
         __syncthreads();
-        const double from = t ? s_end[t - 1] : 0.0;
+        const double from = s_prev[t] >= 0 ? s_end[s_prev[t]] : 0.0;
         const bool redo = __double_as_longlong(from) != __double_as_longlong(start);
-        if (!__syncthreads_or(redo)) break;            // also orders the reads of s_end before the next round's writes
+        const int n_redo = __syncthreads_count(redo);      // also orders the reads of s_end before the next round's writes
+        if (!n_redo) break;
+        if (repairs >= max_repairs || (repairs >= 2 && 2 * n_redo > S)) { stuck = 1; break; }   // over budget / not settling
+        ++repairs;
         if (redo) {
             double b = from;
-            if (!chain_walk<true>(c, b0, b1, start, b)) end = b;
+            if (!chain_walk<true>(c, b0, b1, start, b, st)) end = b;
             start = from;
         }
+    }
+    // A chain that will not settle is strictly sequential: with two warps or more the CTA turns into one producer /
+    // consumer pair of the queue kernel on the spot (the other chains of the launch keep repairing meanwhile);
+    // a single-warp CTA leaves it to the filtered k_att_chain launch that follows.
+    const bool here = stuck && S >= 64;
+    if (t == 0) gave_up[blockIdx.x] = stuck && !here;
+    if (here && t < 64) {
+        extern __shared__ __align__(16) unsigned char s_raw[];
+        chain_queue_run(job, *reinterpret_cast<ChainSmem *>(s_raw), t >= 32, t & 31, 1, rms, tables, ckpt, att_f, mb_frames);
     }
 }
 

@@ -170,6 +170,15 @@ class MasterPlan:
         names = [self.lib.ame_kernel_name(i).decode() for i in range(L.AME_N_KERNELS)]
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}, steps.value
 
+    def wave_timeline(self):
+        """Rows (h2d_done, kernels_may_start, kernels_done, d2h_done) in ms, one per wave, of the last master_host()
+        made with timing enabled."""
+        buf = (C.c_float * (4 * 256))()
+        n = self.lib.ame_plan_wave_timeline(self.handle, buf, 256)
+        if n < 0:
+            L.check(n)
+        return [tuple(buf[4 * w + k] for k in range(4)) for w in range(n)]
+
     # stage entry points (parity taps)
     def stage_eq(self, d_in, d_pre, stream=None):
         L.check(self.lib.ame_stage_eq(self.handle, self._ptr(d_in), self._ptr(d_pre), C.c_void_p(stream or 0)))

@@ -160,6 +160,10 @@ int32_t ame_plan_wave_count(const ame_plan *plan);
 int ame_plan_set_timing(ame_plan *plan, int enable);
 int ame_plan_kernel_times(ame_plan *plan, double *ms_sum, int64_t *launches, int *n_steps);
 const char *ame_kernel_name(int slot);
+/* timeline of the last ame_master_host call made with timing enabled: for each wave, milliseconds since the call's
+ * first copy was queued at which {its H2D copy finished, its kernels could start, its kernels finished, its D2H copy
+ * finished}.  ms holds 4 * max_waves floats; returns the number of waves written, or a negative error. */
+int ame_plan_wave_timeline(ame_plan *plan, float *ms, int max_waves);
 
 /* the whole path: replaces the chunk loop + concat + loudnorm of
  * process_audio_with_ffmpeg_pipeline (:185-220).  d_in / d_out are DEVICE pointers to packed
