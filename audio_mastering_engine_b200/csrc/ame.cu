@@ -321,17 +321,16 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
     return AME_OK;
 }
 
-// k_att_chain_spec or k_att_chain?  The speculative kernel cuts the latency of a chain ~6x (32..256 lanes walk it)
-// but pays an uncoalesced 32-byte table gather and an 8-byte store per flagged frame and lane: ~36 us of machine time
-// per 30 s chain, against a flat ~13 ms for ANY number of chains up to 8 per SM with the queue kernel, which keeps
-// one lane per chain busy and leaves the machine to the other streams (profiles/r01e_summary.md).  So: speculative
-// for small plans, queue kernel for batches.  Returns the threads per chain of the speculative kernel, 0 = queue.
+// Threads per chain of k_att_chain_spec (32 speculative time segments per warp), 0 = the queue kernel k_att_chain
+// alone.  Measured on the bench batch (profiles/r01e_summary.md): 2 warps per chain for launches of 192..1152 chains
+// (33.6 ms/step against 40.0 with the queue kernel and 40.8 with one warp, which cannot redo a stuck chain in place),
+// 4 warps for the 36-chain waves of the host path (99.6 ms end to end against 107) and for a single track; 8 warps
+// cut the segments so short that the extra repair passes cost more than they save.
 int chain_threads(const ame_plan *p, int n_chains) {
     if (p->chain_warps < 0) return 0;
     if (p->chain_warps > 0) return 32 * p->chain_warps;
-    if (p->all.chain_n > p->n_sm) return 0;
-    const int warps = p->n_sm / (2 * std::max(n_chains, 1));
-    return 32 * std::max(2, std::min(warps, kChainMaxThreads / 32));   // >= 2 warps: a chain that will not settle is redone in place
+    const int warps = p->n_sm / std::max(n_chains, 1);
+    return 32 * std::max(2, std::min(warps, 4));
 }
 
 int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_pre, cudaStream_t s) {

@@ -30,9 +30,9 @@ METRIC = "audio-sec mastered/sec (x realtime)"
 UNIT = "x realtime"
 B_ALG_CHAIN = 16       # bytes per stereo frame, whole chain with normalisation
 # DRAM bytes per launch measured once with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum) on the
-# 128-track workload with ONE plan wave; scaled by 1 / waves below.  Source: profiles/r01d_summary.md (prof9).
-KERNEL_NCU_TRAFFIC_1WAVE = {"k_eq": 9.244e9, "k_band_split": 9.595e9, "k_window_flag": 9.945e9, "k_att_chain": 4.379e9,
-                            "k_compress_apply": 13.269e9, "k_kweight_energy": 6.366e9}
+# 128-track workload with ONE plan wave; scaled by 1 / waves below.  Source: profiles/r01e_summary.md.
+KERNEL_NCU_TRAFFIC_1WAVE = {"k_eq": 9.242e9, "k_band_split": 9.343e9, "k_window_flag": 9.941e9, "k_att_chain": 6.591e9,
+                            "k_compress_apply": 13.273e9, "k_kweight_energy": 6.363e9}
 KERNEL_ALG_BYTES = {   # per-kernel algorithmic bytes per frame it processes
     "k_eq": 8, "k_band_split": 16, "k_window_flag": 18, "k_att_chain": 6, "k_compress_apply": 22,
     "k_kweight_energy": 4, "k_apply_gain": 8}
@@ -276,7 +276,7 @@ def run_b200(args, rank, world, local_rank):
             per_kernel_roof[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4)}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic / max(args.waves, 1)) if traffic else None,
-                "traffic_source": "ncu --set full on this workload, 1 plan wave, divided by waves (profiles/r01d_summary.md)" if traffic else None,
+                "traffic_source": "ncu --set full on this workload, 1 plan wave, divided by waves (profiles/r01e_summary.md)" if traffic else None,
                 "peak_source": peak_src, "kernel_ms": per_kernel[dom], "per_kernel": per_kernel_roof,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "chain": {"achieved": chain_gbs, "frac": chain_gbs / peak, "bytes_per_frame": B_ALG_CHAIN},

@@ -128,8 +128,9 @@ typedef struct {
                                     of one wave overlaps the bulk kernels of the others, and ame_master_host also
                                     overlaps the H2D copy of wave w+1 and the D2H copy of wave w-1 with the kernels of
                                     wave w.  Tiles shrink with the wave, so more waves = more filter warm-up work */
-    int32_t chain_warps;         /* compressor recurrence: 0 = choose per launch; 1..8 = k_att_chain_spec with that many warps
-                                    (x32 speculative time segments) per chain; -1 = k_att_chain (one lane per chain) */
+    int32_t chain_warps;         /* compressor recurrence: 0 = k_att_chain_spec with 2..4 warps (x32 speculative time
+                                    segments) per chain, chosen per launch; 1..8 = that many warps; -1 = k_att_chain
+                                    alone (one lane per chain, the sequential form) */
 } ame_plan_options;
 
 typedef struct ame_plan ame_plan;
