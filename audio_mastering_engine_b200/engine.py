@@ -255,6 +255,33 @@ def master(samples, fs, settings, device=0, chunk_seconds=30, **plan_opts):
     return (outs[0], infos[0]) if single else (outs, infos)
 
 
+def bind_host_to_gpu_numa(device=0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers it allocates
+    afterwards (and the threads that fill them) are local to the GPU's PCIe root: with one process per GPU on a
+    two-socket box, buffers that all land on socket 0 send half of the H2D / D2H traffic across the socket link.
+    Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        name = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{name}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # file boundary: stdlib wave instead of ffmpeg / pydub (SURVEY.md 8(f) row 2)
 # ------------------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -155,12 +156,13 @@ def run_reference(args, rank, world):
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from audio_mastering_engine_b200 import MasterPlan, synth, EQ_PRESETS
+    from audio_mastering_engine_b200 import MasterPlan, synth, EQ_PRESETS, bind_host_to_gpu_numa
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None if args.no_numa_bind else bind_host_to_gpu_numa(local_rank)   # before any pinned allocation
     if world > 1:
         # NCCL writes its version banner to stdout when the communicator is created: send fd 1 to stderr until the
         # first collective is through, so that stdout carries nothing but the one JSON line
@@ -248,7 +250,7 @@ def run_b200(args, rank, world, local_rank):
         same = bool(torch.equal(h_out.to(dev), d_out))
         e2e = {"value": world * audio_rank * args.e2e_steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h_in.numel() * 2), "d2h_bytes_per_step": int(h_out.numel() * 2 + 48 * n_tr),
-               "steps": args.e2e_steps, "waves": args.e2e_waves, "matches_device_path": same,
+               "steps": args.e2e_steps, "waves": args.e2e_waves, "numa_node": numa_node, "matches_device_path": same,
                "first_track_lufs": res[0]["input_i"]}
         hplan.close()
         del h_in, h_out
