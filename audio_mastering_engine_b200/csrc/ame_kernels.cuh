@@ -401,6 +401,16 @@ __device__ __forceinline__ void load8(const uint32_t *__restrict__ p, int64_t id
     }
 }
 
+// floor(sqrt(s / n)) in exact integers, for s / n < 2^31 and n < 2^11: audioop.rms is (unsigned)sqrt(S / n) in double,
+// which truncates to exactly this (header comment above) - a float estimate is within 1 of it, two integer tests
+// settle it, and the double division + square root (~55 instructions on the FP64 pipe per flagged frame) go away.
+__device__ __forceinline__ unsigned isqrt_ratio(unsigned long long s, unsigned n) {
+    unsigned r = (unsigned)__fsqrt_rn(__fdividef((float)s, (float)n));
+    if ((unsigned long long)r * r * n > s) --r;
+    else if ((unsigned long long)(r + 1) * (r + 1) * n <= s) ++r;
+    return r;
+}
+
 __global__ void __launch_bounds__(kWfThreads)
 k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chains, const int16_t *__restrict__ bands,
               uint16_t *__restrict__ rms, int64_t mb_frames) {
@@ -460,7 +470,7 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
         const int64_t nfr = i < look ? i : look;
         unsigned r = 0;
         if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
-            r = __double2uint_rz(__dsqrt_rn(__ddiv_rn((double)s, (double)(2 * nfr))));
+            r = isqrt_ratio((unsigned long long)s, (unsigned)(2 * nfr));
         o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
     }
     if (i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(rp + i0) & 15) == 0)) {
