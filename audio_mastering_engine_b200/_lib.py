@@ -59,6 +59,7 @@ SYMBOLS = {
     "ame_abi_version": (C.c_int, []),
     "ame_sizeof_track_params": (C.c_size_t, []),
     "ame_sizeof_track_result": (C.c_size_t, []),
+    "ame_sizeof_plan_options": (C.c_size_t, []),
     "ame_last_error": (C.c_char_p, []),
     "ame_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ame_plan_create": (C.c_int, [C.c_int, C.POINTER(TrackParams), C.c_int32, C.POINTER(PlanOptions), C.POINTER(C.c_void_p)]),
@@ -103,7 +104,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.ame_sizeof_track_params() != C.sizeof(TrackParams) or lib.ame_sizeof_track_result() != C.sizeof(TrackResult):
+        if (lib.ame_sizeof_track_params() != C.sizeof(TrackParams) or lib.ame_sizeof_track_result() != C.sizeof(TrackResult)
+                or lib.ame_sizeof_plan_options() != C.sizeof(PlanOptions)):
             raise AmeError("ctypes structs are out of sync with include/ame.h")
         _lib = lib
     return _lib

@@ -413,6 +413,7 @@ extern "C" {
 int ame_abi_version(void) { return AME_ABI_VERSION; }
 size_t ame_sizeof_track_params(void) { return sizeof(ame_track_params); }
 size_t ame_sizeof_track_result(void) { return sizeof(ame_track_result); }
+size_t ame_sizeof_plan_options(void) { return sizeof(ame_plan_options); }
 const char *ame_last_error(void) { return g_err.c_str(); }
 const char *ame_kernel_name(int slot) { return (slot >= 0 && slot < AME_N_KERNELS) ? kKernelNames[slot] : ""; }
 

@@ -356,13 +356,18 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
 // Multiband compressor = pydub compress_dynamic_range per band (:306-308), split by what is sequential:
 //   k_window_flag   (time-parallel)  window rms of the previous look_frames frames; emits the integer rms
 //                                    for frames ABOVE threshold and 0 otherwise (2 B per band frame)
-//   k_att_chain     (sequential)     one warp per (chunk, band): walks ONLY the flagged frames and runs the
-//                                    attenuation recurrence; emits the attenuation entering each 32-frame
-//                                    group (8 B per group).  Below threshold the reference never releases
+//   k_att_chain_spec (speculative)   the attenuation recurrence over the flagged frames of one (chunk, band), cut
+//                                    into 64..256 time segments that are walked in parallel from a guessed start
+//                                    and repaired until every segment starts from its predecessor's true end
+//                                    (exact); emits the attenuation after every flagged frame and entering each
+//                                    32-frame group.  Below threshold the reference never releases
 //                                    (max_attenuation = 0 => dec = 0), so unflagged frames are no-ops.
-//   k_compress_apply (time-parallel) per 32-frame group: replay the recurrence inside the group from its
-//                                    entry value (bit-identical arithmetic), gain = 10^(-att/20),
-//                                    audioop.mul, and low.overlay(mid).overlay(high) (:309) into `pre`.
+//   k_att_chain      (sequential)    the same recurrence by one producer + one consumer warp per chain: the
+//                                    fallback for chains whose segments cannot be repaired cheaply, and the
+//                                    whole stage with chain_warps = -1.
+//   k_compress_apply (time-parallel) attenuation in force at a frame = the value stored for the last flagged frame
+//                                    at or before it in its 32-frame group, else the group's entry value;
+//                                    gain = 10^(-att/20), audioop.mul, low.overlay(mid).overlay(high) (:309).
 // pydub: rms_at(i) = audioop.rms(frames [max(i-look,0), i)) = (unsigned)sqrt(S / n) with S the exact integer
 // sum of squares and n = 2 * frames.  rms > thresh  <=>  rms >= thr_i  <=>  S >= thr_i^2 * n (integers), so
 // only flagged frames take the square root (S/n is never within 2^-41 of a perfect square unless equal,

@@ -139,6 +139,7 @@ typedef struct ame_plan ame_plan;
 int ame_abi_version(void);
 size_t ame_sizeof_track_params(void);
 size_t ame_sizeof_track_result(void);
+size_t ame_sizeof_plan_options(void);
 const char *ame_last_error(void);             /* thread-local text of the last failure */
 int ame_device_count(int *count);
 

@@ -34,6 +34,7 @@ def test_struct_layout_matches(lib):
     from audio_mastering_engine_b200 import _lib
     assert lib.ame_sizeof_track_params() == ctypes.sizeof(_lib.TrackParams)
     assert lib.ame_sizeof_track_result() == ctypes.sizeof(_lib.TrackResult)
+    assert lib.ame_sizeof_plan_options() == ctypes.sizeof(_lib.PlanOptions)
 
 
 def test_no_cpu_fallback(lib):
