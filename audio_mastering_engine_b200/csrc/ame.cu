@@ -323,9 +323,9 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
 
 // Threads per chain of k_att_chain_spec (32 speculative time segments per warp), 0 = the queue kernel k_att_chain
 // alone.  Measured on the bench batch (profiles/r01e_summary.md): 2 warps per chain for launches of 192..1152 chains
-// (33.6 ms/step against 40.0 with the queue kernel and 40.8 with one warp, which cannot redo a stuck chain in place),
-// 4 warps for the 36-chain waves of the host path (99.6 ms end to end against 107) and for a single track; 8 warps
-// cut the segments so short that the extra repair passes cost more than they save.
+// (33.5 ms/step against 40.0 with the queue kernel and 37.4 with 32 segments), 4 warps for the 36-chain waves of the
+// host path (99.6 ms end to end against 107) and for a single track; 8 warps cut the segments so short that the
+// extra repair passes cost more than they save.  The CTA always has two warps or more (in-place fallback).
 int chain_threads(const ame_plan *p, int n_chains) {
     if (p->chain_warps < 0) return 0;
     if (p->chain_warps > 0) return 32 * p->chain_warps;
@@ -342,8 +342,9 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
     t_begin(p, S_CHAIN, s);
     const int ct = chain_threads(p, w.chain_n);
     if (ct) {
-        k_att_chain_spec<<<w.chain_n, ct, ct >= 64 ? sizeof(ChainSmem) : 0, s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames,
-                                                  p->d_chain_stuck + w.chain_lo);
+        // at least two warps, so that a chain that will not settle can be redone in place
+        k_att_chain_spec<<<w.chain_n, std::max(ct, 64), sizeof(ChainSmem), s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf,
+                                                                                p->mb_frames, p->d_chain_stuck + w.chain_lo, ct);
         LAUNCH_CHECK(p);
     }
     // the queue kernel: every chain, or (after the speculative kernel) only those it flagged - a CTA without one exits at once

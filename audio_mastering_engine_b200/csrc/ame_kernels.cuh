@@ -799,12 +799,13 @@ __device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_
 
 __global__ void __launch_bounds__(kChainMaxThreads)
 k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
-                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames, int *__restrict__ gave_up) {
+                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames, int *__restrict__ gave_up,
+                 int n_lanes) {            // segments per chain (<= blockDim.x; threads past it only serve the fallback)
     __shared__ double s_end[kChainMaxThreads], s_max_m[kChainMaxThreads], s_dec[kChainMaxThreads];
     __shared__ int s_nflag[kChainMaxThreads], s_ngrp[kChainMaxThreads], s_stuck, s_budget;
     __shared__ short s_prev[kChainMaxThreads];
     const ChainJob job = jobs[blockIdx.x];
-    const int S = blockDim.x, t = threadIdx.x;
+    const int S = n_lanes, t = threadIdx.x;     // threads t >= S get an empty segment [n, n)
     ChainCtx c;
     c.rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
     c.tbl = tables + (size_t)job.table * 32769;
@@ -863,7 +864,7 @@ k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__
         s_end[t] = end;
         __syncthreads();
         const double from = s_prev[t] >= 0 ? s_end[s_prev[t]] : 0.0;
-        const bool redo = __double_as_longlong(from) != __double_as_longlong(start);
+        const bool redo = t < S && __double_as_longlong(from) != __double_as_longlong(start);
         const int n_redo = __syncthreads_count(redo);      // also orders the reads of s_end before the next round's writes
         if (!n_redo) break;
         if (repairs >= max_repairs || (repairs >= 2 && 2 * n_redo > S)) { stuck = 1; break; }   // over budget / not settling
@@ -877,7 +878,7 @@ k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__
     // A chain that will not settle is strictly sequential: with two warps or more the CTA turns into one producer /
     // consumer pair of the queue kernel on the spot (the other chains of the launch keep repairing meanwhile);
     // a single-warp CTA leaves it to the filtered k_att_chain launch that follows.
-    const bool here = stuck && S >= 64;
+    const bool here = stuck && blockDim.x >= 64;
     if (t == 0) gave_up[blockIdx.x] = stuck && !here;
     if (here && t < 64) {
         extern __shared__ __align__(16) unsigned char s_raw[];
