@@ -685,7 +685,7 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
 }
 
 // k_att_chain_spec: the recurrence, made parallel in time by SPECULATION AND REPAIR - exact, not approximate.
-// One CTA per (chunk, band); its S = blockDim.x threads cut the chunk into S contiguous segments and every lane
+// One CTA per (chunk, band); S = n_lanes of its threads cut the chunk into S contiguous segments and every lane
 // walks its own segment (the lanes of a warp run in lockstep, so a step of the 25-cycle dependent chain advances
 // 32 segments at once):
 //   pass 1   every lane starts from attenuation 0 (lane 0 really does - the reference resets it per chunk);
@@ -696,7 +696,8 @@ k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__res
 //            never meets publishes a new end value;
 //   until no lane's start changed.  By induction every lane has then been walked from the true end of its
 //   predecessor, i.e. the stored values are those of the sequential loop.  A chain that does not settle within its
-//   repair budget is flagged in gave_up[] and recomputed by k_att_chain (launched right after, filtered by the flags).
+//   repair budget is redone by two warps of the CTA as the producer / consumer pair of k_att_chain (or, from a
+//   one-warp CTA, flagged in gave_up[] for the filtered k_att_chain launch that follows).
 // Trajectories meet whenever both clamp to the same max_attenuation (att in [tau, M] -> M), which the compressor
 // does all the time while it tracks the level: on the bench tracks 0.3k-20k frames after a segment start (two or
 // three passes).  A signal that never clamps would degrade to one segment per pass; the budget below cuts that off.
@@ -822,8 +823,8 @@ k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__
     // What the first walk tells, before any repair is paid for (thread 0, S <= 256 segments):
     // * budget.  Measured on B200 (profiles/r01e_summary.md): a repair pass costs a lone warp ~120 cycles per frame of
     //   every 8-frame group that holds a flagged frame (the walk skips the others; the slowest lane carries ~1.3x the
-    //   mean) plus ~5 per frame of the segment for scanning; the queue kernel, which compacts the flagged frames, 25 cycles per
-    //   flagged frame plus ~4 per frame.  Speculation may cost 80 % of what the queue kernel needs for the chain: a
+    //   mean) plus ~5 per frame of the segment for scanning; the queue kernel, which compacts the flagged frames,
+    //   25 cycles per flagged frame plus ~4 per frame.  Speculation may cost 80 % of what the queue kernel needs for the chain: a
     //   band at 12 % flagged frames spread over every group is cheap for the queue and dear to repair, one at 40 %
     //   in bursts the other way round.
     // * forecast.  Follow a lower bound of the TRUE attenuation through the segments: where it enters a segment above
