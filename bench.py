@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
+    ap.add_argument("--kw-tile", type=int, default=0, help="ame_plan_options.kw_tile_subblocks (0 = auto)")
+    ap.add_argument("--eq-tile", type=int, default=0, help="ame_plan_options.eq_tile_frames (0 = auto)")
+    ap.add_argument("--xover-tile", type=int, default=0, help="ame_plan_options.xover_tile_frames (0 = auto)")
     return ap.parse_args()
 
 
@@ -193,7 +196,8 @@ def run_b200(args, rank, world, local_rank):
     nb = [t for t in ids if not synth.c4_settings(t, EQ_PRESETS)["multiband"]]
     ids = nb[:2] + mb + nb[2:]
     settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
-    plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves, chain_warps=args.chain_warps)
+    plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves, chain_warps=args.chain_warps,
+                      kw_tile_subblocks=args.kw_tile, eq_tile_frames=args.eq_tile, xover_tile_frames=args.xover_tile)
     assert plan.total_frames == n_tr * ((n + 7) // 8 * 8)
     tracks = synth.torch_track_batch(n_tr, secs, fs, dev, first_track_id=first)        # [n_tr, n, 2] int16
     d_in = torch.zeros((plan.total_frames, 2), dtype=torch.int16, device=dev)
