@@ -168,6 +168,8 @@ def track_params(settings, fs, n_frames, offset_frames=0, chunk_seconds=30, lut_
     """Fill one ame_track_params from a reference-style settings dict.  `lut_index` maps
     analog_character -> table index and is extended in place."""
     fs = int(fs)
+    if fs < 4000:       # the BS.1770 pre-filter sits at 1682 Hz: below ~3.4 kHz sampling it is not a filter any more
+        raise ValueError(f"unsupported sample rate {fs} Hz")
     p = L.TrackParams()
     p.offset_frames, p.n_frames, p.sample_rate = int(offset_frames), int(n_frames), fs
     p.halo_frames = int(halo_frames)

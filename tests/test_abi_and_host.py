@@ -68,6 +68,21 @@ def test_design_matches_reference_recipe():
     assert p.warm_eq > 1000 and p.warm_xover > 1000 and p.warm_kw > 3000
     flat = design.track_params({"lufs": None}, 48000, 10, 0, 30, {})
     assert flat.flags == 0 and all(flat.eq[i].kind == 0 for i in range(4)) and flat.warm_eq == 0
+    with pytest.raises(ValueError, match="unsupported sample rate"):
+        design.track_params({"lufs": -14.0}, 1000, 10, 0, 30, {})
+    with pytest.raises(TypeError):        # multiband without its thresholds: pydub would raise too
+        design.track_params({"multiband": True}, 48000, 10, 0, 30, {})
+
+
+def test_bind_host_to_gpu_numa_is_harmless_without_topology():
+    """No GPU / no sysfs topology: returns None and leaves the CPU affinity alone."""
+    import os
+    from audio_mastering_engine_b200 import bind_host_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    node = bind_host_to_gpu_numa(0)
+    assert node is None or isinstance(node, int)
+    if node is None:
+        assert os.sched_getaffinity(0) == before
 
 
 def test_k_weighting_biquads_are_bs1770():
