@@ -817,7 +817,18 @@ k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__
     // whole 32-frame groups per segment: a checkpoint and a 32-byte rms load never straddle two lanes
     const int64_t seg = (((c.n + S - 1) / S) + 31) & ~(int64_t)31;
     const int64_t b0 = min(c.n, (int64_t)t * seg), b1 = min(c.n, b0 + seg);
-    double start = 0.0, end = 0.0;
+    // First guess for the attenuation entering the segment: the max_attenuation of the last flagged frame before it
+    // (looked for in the 64 frames in front), which is exactly right whenever the compressor was clamped to it there -
+    // about every second frame while it tracks a rising level - and costs nothing when it is wrong; else 0.
+    double start = 0.0;
+    if (t > 0 && t < S && b0 < b1) {
+        const int64_t lo = max((int64_t)0, b0 - 64);
+        for (int64_t i = b0 - 1; i >= lo; --i) {
+            const unsigned r = __ldg(c.rp + i);
+            if (r) { start = c.tbl[r].m; break; }
+        }
+    }
+    double end = start;
     SegStat st{0.0, 0.0, 0, 0};
     chain_walk<false>(c, b0, b1, 0.0, end, st);
     // What the first walk tells, before any repair is paid for (thread 0, S <= 256 segments):

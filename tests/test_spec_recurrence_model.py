@@ -1,6 +1,6 @@
 """Host-side model of the algorithm inside k_att_chain_spec (csrc/ame_kernels.cuh): the compressor's attenuation
 recurrence evaluated in S time segments from guessed starts and repaired until exact.  The model restates the
-kernel's control flow in Python - pass 1 from zero, repair passes that carry the old and the new start and stop
+kernel's control flow in Python - pass 1 from a guessed start, repair passes that carry the old and the new start and stop
 where they are equal, starts handed across silent segments - and checks the claim the kernel relies on: when no
 segment's start changes any more, every stored value is the one the sequential loop (pydub's, oracle/chain.py)
 produces, bit for bit; and the tau form of the update used on the GPU is the reference's update.
@@ -80,8 +80,13 @@ def _speculative(rms, thr, entry, n_seg):
     start = [0.0] * n_seg
     end = [0.0] * n_seg
     flagged = [bool(np.any(rms[b0:b1] > thr)) for b0, b1 in bounds]
-    for t, (b0, b1) in enumerate(bounds):                       # pass 1
-        end[t], _ = _walk(rms, thr, entry, b0, b1, 0.0, out)
+    for t, (b0, b1) in enumerate(bounds):                       # pass 1, from a guess: M of the last flagged frame in front
+        if t > 0 and b0 < b1:
+            for i in range(b0 - 1, max(0, b0 - 64) - 1, -1):
+                if rms[i] > thr:
+                    start[t] = entry(int(rms[i]))[0]
+                    break
+        end[t], _ = _walk(rms, thr, entry, b0, b1, start[t], out)
     prev = []
     for t in range(n_seg):                                      # last segment before t that holds a flagged frame
         u = t - 1
@@ -128,7 +133,7 @@ def test_speculate_and_repair_equals_sequential(kind, n_seg):
     got, passes = _speculative(rms, thr, entry, n_seg)
     assert np.array_equal(got, want), (kind, n_seg)
     if kind == "held" and n_seg > 1:
-        assert passes >= n_seg - 1           # the strictly sequential case: one segment settles per pass
+        assert passes >= n_seg // 2          # the strictly sequential case: about one segment settles per pass
 
 
 def test_tau_form_is_the_reference_update():
