@@ -62,6 +62,7 @@ SYMBOLS = {
     "ame_sizeof_plan_options": (C.c_size_t, []),
     "ame_last_error": (C.c_char_p, []),
     "ame_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ame_release_cached_memory": (C.c_int, [C.c_int]),
     "ame_plan_create": (C.c_int, [C.c_int, C.POINTER(TrackParams), C.c_int32, C.POINTER(PlanOptions), C.POINTER(C.c_void_p)]),
     "ame_plan_destroy": (None, [C.c_void_p]),
     "ame_plan_set_warm_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -36,12 +37,58 @@ int fail(int code, const char *fmt, ...) {
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Device memory comes from one stream-ordered pool per device whose release threshold is lifted: the workspace of a
+// destroyed plan stays in the pool and the next plan gets it back in microseconds.  (cudaMalloc + cudaFree of the
+// ~25 buffers of a plan cost 50 - 150 ms, several times what mastering a 3 min track takes; profiles/r01e_summary.md.)
+// Allocation and release are ordered on the legacy default stream, which every entry point that allocates
+// synchronises before it returns; ame_release_cached_memory() hands the pool back to the driver.
+constexpr int kMaxDevices = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[kMaxDevices] = {};
+bool g_pool_tried[kMaxDevices] = {};
+
+cudaMemPool_t device_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool_tried[dev]) {
+        g_pool_tried[dev] = true;
+        int ok = 0;
+        cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev);
+        if (ok) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            unsigned long long keep = ~0ull;
+            if (cudaMemPoolCreate(&pool, &props) == cudaSuccess &&
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess)
+                g_pools[dev] = pool;
+            else
+                cudaGetLastError();
+        }
+    }
+    return g_pools[dev];
+}
+
+cudaError_t dev_alloc(void **ptr, size_t bytes) {
+    if (cudaMemPool_t pool = device_pool()) return cudaMallocFromPoolAsync(ptr, bytes, pool, 0);
+    return cudaMalloc(ptr, bytes);
+}
+
+void dev_free(void *ptr) {
+    if (!ptr) return;
+    if (device_pool()) cudaFreeAsync(ptr, 0); else cudaFree(ptr);
+}
+
 template <class T>
 int upload(T **dptr, const std::vector<T> &v) {
     *dptr = nullptr;
     if (v.empty()) return AME_OK;
-    cudaError_t e = cudaMalloc((void **)dptr, v.size() * sizeof(T));
-    if (e != cudaSuccess) return fail(AME_E_NOMEM, "cudaMalloc(%zu) failed: %s", v.size() * sizeof(T), cudaGetErrorString(e));
+    cudaError_t e = dev_alloc((void **)dptr, v.size() * sizeof(T));
+    if (e != cudaSuccess) return fail(AME_E_NOMEM, "device allocation of %zu bytes failed: %s", v.size() * sizeof(T), cudaGetErrorString(e));
     CU(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return AME_OK;
 }
@@ -135,8 +182,8 @@ inline void t_end(ame_plan *p, int kernel, cudaStream_t s) {
 int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
     *ptr = nullptr;
     if (bytes == 0) return AME_OK;
-    cudaError_t e = cudaMalloc(ptr, bytes);
-    if (e != cudaSuccess) return fail(AME_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cudaError_t e = dev_alloc(ptr, bytes);
+    if (e != cudaSuccess) return fail(AME_E_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     p->ws_bytes += bytes;
     return AME_OK;
 }
@@ -432,8 +479,8 @@ void ame_plan_destroy(ame_plan *p) {
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
                     p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results,
                     p->d_chain_stuck};
-    for (void *q : ptrs)
-        if (q) cudaFree(q);
+    cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
+    for (void *q : ptrs) dev_free(q);
     for (cudaStream_t s : {p->s_in, p->s_out})
         if (s) cudaStreamDestroy(s);
     for (cudaStream_t s : p->s_run) cudaStreamDestroy(s);
@@ -740,20 +787,29 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             cudaMemcpyToSymbol(c_hist_energy, energies, sizeof energies) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
+    CU(cudaStreamSynchronize(0));       // allocations are ordered on the default stream; the plan runs on others
     *out = p;
+    return AME_OK;
+}
+
+int ame_release_cached_memory(int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    if (cudaMemPool_t pool = device_pool()) CU(cudaMemPoolTrimTo(pool, 0));
     return AME_OK;
 }
 
 int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
     if (!p || !luts || n_luts <= 0) return fail(AME_E_INVALID, "bad warm lut arguments");
     CU(cudaSetDevice(p->device));
-    if (p->d_luts) { cudaFree(p->d_luts); p->d_luts = nullptr; }
+    if (p->d_luts) { CU(cudaDeviceSynchronize()); dev_free(p->d_luts); p->d_luts = nullptr; }
     // widened exactly to double on the host so the kernel needs no float->double conversion per sample
     std::vector<double> wide((size_t)n_luts * 65536);
     for (size_t i = 0; i < wide.size(); ++i) wide[i] = (double)luts[i];
     int rc = dmalloc(p, (void **)&p->d_luts, wide.size() * sizeof(double));
     if (rc) return rc;
     CU(cudaMemcpy(p->d_luts, wide.data(), wide.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(0));
     p->n_luts = n_luts;
     return AME_OK;
 }

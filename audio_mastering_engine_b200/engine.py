@@ -244,15 +244,26 @@ def master(samples, fs, settings, device=0, chunk_seconds=30, **plan_opts):
     plan = MasterPlan([t.shape[0] for t in tracks], fs_list, st_list, device=device, chunk_seconds=chunk_seconds,
                       host_io=True, **plan_opts)
     try:
-        h_in = plan.pack(tracks)
-        h_out = np.empty_like(h_in)
-        infos = plan.master_host(h_in, h_out)
-        outs = plan.unpack(h_out)
+        if n == 1 and plan.total_frames == tracks[0].shape[0]:     # one track that is its own packed buffer: no copies
+            h_out = np.empty_like(tracks[0])
+            infos = plan.master_host(tracks[0], h_out)
+            outs = [h_out]
+        else:
+            h_in = plan.pack(tracks)
+            h_out = np.empty_like(h_in)
+            infos = plan.master_host(h_in, h_out)
+            outs = plan.unpack(h_out)
         for i in infos:
             i["launches"] = plan.launch_count
     finally:
         plan.close()
     return (outs[0], infos[0]) if single else (outs, infos)
+
+
+def release_cached_memory(device=0):
+    """Plans take their workspace from a per-device pool that keeps the memory of closed plans for the next one;
+    this hands it back to the driver."""
+    L.check(L.load().ame_release_cached_memory(int(device)))
 
 
 def bind_host_to_gpu_numa(device=0):

@@ -142,6 +142,9 @@ size_t ame_sizeof_track_result(void);
 size_t ame_sizeof_plan_options(void);
 const char *ame_last_error(void);             /* thread-local text of the last failure */
 int ame_device_count(int *count);
+/* plan workspaces are taken from a per-device memory pool that keeps the memory of destroyed plans for the next one
+ * (creating and destroying a plan per track then costs microseconds instead of ~100 ms); this returns it to the driver */
+int ame_release_cached_memory(int device);
 
 /* plan: geometry + coefficients + workspace for one batch on one device ------------------------- */
 int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks,
