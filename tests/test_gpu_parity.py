@@ -345,3 +345,19 @@ def test_compressor_kernels_agree(torch_cuda):
             out, info = master(x, fs, s, chunk_seconds=chunk, chain_warps=cw)
             assert np.array_equal(out, base), cw
             assert info["input_i"] == binfo["input_i"]
+
+
+def test_plan_memory_pool_reuse_and_release(torch_cuda):
+    """Plan workspaces come from a per-device pool that keeps the memory of destroyed plans: results must not depend
+    on whether a plan got fresh or recycled (dirty) memory, and the pool can be handed back at any time."""
+    from audio_mastering_engine_b200 import master, release_cached_memory, synth
+    fs = 48000
+    x = synth.track(2.0, fs, track_id=21, am_hz=3.0)              # 96000 frames: the zero-copy single-track path
+    y = synth.track(1.3, fs, track_id=22, am_hz=2.0)[:62001]      # ragged: the packed path
+    first = [master(x, fs, synth.c2_settings(), chunk_seconds=1)[0], master(y, fs, synth.c1_settings())[0]]
+    master([x, y, x], fs, [synth.c1_settings(), synth.c2_settings(), synth.c2_settings()], chunk_seconds=0.5)   # dirties a larger workspace
+    again = [master(x, fs, synth.c2_settings(), chunk_seconds=1)[0], master(y, fs, synth.c1_settings())[0]]
+    release_cached_memory(0)
+    fresh = [master(x, fs, synth.c2_settings(), chunk_seconds=1)[0], master(y, fs, synth.c1_settings())[0]]
+    for a, b, c in zip(first, again, fresh):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
