@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libame.so")
 AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE = 1, 2, 4, 8
 AME_N_KERNELS = 10
 AME_EQ_BYPASS, AME_EQ_SHELF_BOOST, AME_EQ_SHELF_CUT, AME_EQ_PEAK = 0, 1, 2, 3
+AME_ABI_VERSION = 5
 
 
 class Biquad(C.Structure):
@@ -45,7 +46,8 @@ class TrackResult(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("eq_tile_frames", C.c_int32), ("xover_tile_frames", C.c_int32), ("kw_tile_subblocks", C.c_int32),
-                ("host_io", C.c_int32), ("n_waves", C.c_int32), ("chain_warps", C.c_int32)]
+                ("host_io", C.c_int32), ("n_waves", C.c_int32), ("chain_warps", C.c_int32), ("n_slots", C.c_int32),
+                ("fuse_kw", C.c_int32), ("precision", C.c_int32)]
 
 
 class AmeError(RuntimeError):
@@ -70,6 +72,9 @@ SYMBOLS = {
     "ame_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "ame_plan_launch_count": (C.c_int64, [C.c_void_p]),
     "ame_plan_wave_count": (C.c_int32, [C.c_void_p]),
+    "ame_plan_slot_count": (C.c_int32, [C.c_void_p]),
+    "ame_plan_chain_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "ame_plan_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ame_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "ame_kernel_name": (C.c_char_p, [C.c_int]),
@@ -108,6 +113,9 @@ def load():
         if (lib.ame_sizeof_track_params() != C.sizeof(TrackParams) or lib.ame_sizeof_track_result() != C.sizeof(TrackResult)
                 or lib.ame_sizeof_plan_options() != C.sizeof(PlanOptions)):
             raise AmeError("ctypes structs are out of sync with include/ame.h")
+        if lib.ame_abi_version() != AME_ABI_VERSION:
+            raise AmeError(f"libame.so has ABI version {lib.ame_abi_version()}, this package needs {AME_ABI_VERSION}: "
+                           "rebuild with `python -m audio_mastering_engine_b200.build --force`")
         _lib = lib
     return _lib
 

@@ -37,6 +37,24 @@ int fail(int code, const char *fmt, ...) {
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Every entry point works on its plan's device and leaves the caller's current device as it found it (a process may
+// drive plans on several GPUs, and torch allocates on the current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define GUARD(dev)                                                                                 \
+    DeviceGuard guard_(dev);                                                                       \
+    if (guard_.err != cudaSuccess) return fail(AME_E_CUDA, "cannot select CUDA device %d: %s", (int)(dev), cudaGetErrorString(guard_.err))
+
 // Device memory comes from one stream-ordered pool per device whose release threshold is lifted: the workspace of a
 // destroyed plan stays in the pool and the next plan gets it back in microseconds.  (cudaMalloc + cudaFree of the
 // ~25 buffers of a plan cost 50 - 150 ms, several times what mastering a 3 min track takes; profiles/r01e_summary.md.)
@@ -109,6 +127,19 @@ struct Wave {
     int eq_lo = 0, eq_n = 0, split_lo = 0, split_n = 0, chain_lo = 0, chain_n = 0, wf_lo = 0, wf_n = 0;
     int chunk_lo = 0, chunk_n = 0, kw_lo = 0, kw_n = 0, gain_lo = 0, gain_n = 0;
     int64_t seg_lo = 0, seg_hi = 0;
+    int slot = 0;                                  // workspace slot (and stream) this wave runs in
+    int64_t mb_frames = 0, n_groups = 0;           // of the wave's own multiband packing
+};
+
+// Per-wave workspace.  A plan has n_slots of them; wave w runs in slot w % n_slots on that slot's stream, so a slot is
+// recycled in stream order and a plan over many waves needs the intermediate buffers of only n_slots waves.
+struct Slot {
+    int16_t *pre = nullptr;      // pre-normalisation int16 of the wave (the signal the reference materialises at the concat)
+    int16_t *bands = nullptr;    // 3 planes of mb_frames frames
+    uint16_t *rms = nullptr;     // 3 planes: integer window rms of flagged frames, compacted in place by k_att_chain
+    GrpRec *grp = nullptr;       // per 32-frame group of every chain
+    double *att = nullptr;       // 3 planes: attenuation after every flagged frame, dense per chain
+    cudaStream_t stream = nullptr;
 };
 
 }  // namespace
@@ -122,8 +153,10 @@ struct ame_plan {
     std::vector<Wave> waves;
     Wave all;                             // the union of all waves
     int64_t total_frames = 0;             // padded
-    int64_t mb_frames = 0;                // padded
-    int64_t n_group_total = 0, n_sb_total = 0;
+    int64_t mb_frames = 0;                // padded; the largest wave's multiband packing = plane stride of every slot
+    int64_t slot_frames = 0, slot_groups = 0;
+    int64_t n_sb_total = 0;
+    std::vector<char> fuse_kw;            // per track: K-weighting runs in the k_eq epilogue
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     int n_sm = 148, chain_warps = 0;      // see chain_threads()
     size_t ws_bytes = 0;
@@ -141,16 +174,15 @@ struct ame_plan {
     AttEntry *d_tables = nullptr;
     double *d_luts = nullptr;
     int n_luts = 0;
-    int16_t *d_pre = nullptr, *d_bands = nullptr, *d_in = nullptr, *d_out = nullptr;
-    uint16_t *d_rms = nullptr;
-    double *d_ckpt = nullptr, *d_attf = nullptr, *d_energy = nullptr;
-    int *d_chain_stuck = nullptr;          // per chain: k_att_chain_spec gave up, k_att_chain redoes it
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    std::vector<Slot> slots;
+    double *d_energy = nullptr;
+    int *d_chain_stats = nullptr;          // per chain: {flagged steps, passes} of the last k_att_chain
     long long *d_hist = nullptr;
     int *d_hist_st = nullptr;               // short-term (3 s) histogram per track, for loudness range
     int *d_peak = nullptr;
     ame_track_result *d_results = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
-    std::vector<cudaStream_t> s_run;                                    // host path: kernels, one stream per wave
     std::vector<cudaEvent_t> ev_in, ev_run;                             // per wave
     // optional per-kernel CUDA-event timing (ame_plan_set_timing)
     bool timing = false;
@@ -189,6 +221,16 @@ int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
 }
 
 // split chunk [cb, ce) into ceil(n / T) near-equal tiles whose interior boundaries are multiples of 8
+// the same with every interior boundary at cb + j * t, t a multiple of `q` frames (tracks whose K-weighting runs in
+// the k_eq epilogue: tiles start on the 100 ms sub-block grid, on which their chunks start too)
+void tile_jobs_grid(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T, int64_t q) {
+    const int64_t n = ce - cb;
+    if (n <= 0) return;
+    const int64_t k = (n + T - 1) / T;
+    const int64_t t = align_up((n + k - 1) / k, q);
+    for (int64_t b = cb; b < ce; b += t) out.push_back(TileJob{cb, b, std::min(b + t, ce), track, variant});
+}
+
 void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T) {
     const int64_t n = ce - cb;
     if (n <= 0) return;
@@ -235,12 +277,13 @@ double eq_cost_per_frame(const ame_track_params &t) {
     if (t.eq[3].kind != AME_EQ_BYPASS) c += 16.0;
     return c;
 }
+constexpr double kEqCostKw = 30.0;                      // K-weighting epilogue: two sections + squares, two channels
 
 // k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
 // both variants one after the other.  Every track therefore gets a whole number of warps, in proportion to its
 // cost (frames x cost per frame), and its 32 * warps jobs are spread over its chunks by length.
 std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<double> &cost,
-                                    int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
+                                    int t_lo, int t_hi, int64_t slots, const std::vector<int64_t> &min_tiles) {
     const int n = (int)chunks.size();
     std::vector<int> warps(n, 0);
     std::vector<double> weight(n, 0.0);
@@ -248,7 +291,7 @@ std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chu
     double wsum = 0;
     for (int t = t_lo; t < t_hi; ++t) {
         int64_t frames = 0, max_jobs = 0;
-        for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tile); }
+        for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tiles[t]); }
         weight[t] = (double)frames * cost[t];
         cap[t] = (int)std::max<int64_t>(1, (max_jobs + 31) / 32);
         wsum += weight[t];
@@ -348,11 +391,35 @@ int check_warmth(const ame_plan *p) {
     return AME_OK;
 }
 
-// ---- stage launches over one wave (or over `all`) ------------------------------------------------
+// ---- stage launches over one wave ------------------------------------------------------------------
+// `pre` is addressed with ABSOLUTE packed-buffer frame indices everywhere: for a slot the pointer handed in is
+// slot.pre - 2 * wave.frame_lo (never dereferenced outside the wave's own range).
+struct Bufs {
+    const int16_t *in = nullptr;
+    int16_t *pre = nullptr, *bands = nullptr, *out = nullptr;
+    uint16_t *rms = nullptr;
+    GrpRec *grp = nullptr;
+    double *att = nullptr;
+    int64_t *hist = nullptr;
+};
+
+Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) {
+    const Slot &sl = p->slots[w.slot];
+    Bufs b;
+    b.in = d_in; b.out = d_out;
+    b.pre = sl.pre - 2 * w.frame_lo;
+    b.bands = sl.bands; b.rms = sl.rms; b.grp = sl.grp; b.att = sl.att;
+    b.hist = (int64_t *)p->d_hist;
+    return b;
+}
+
 int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cudaStream_t s) {
+    const int nt = w.track_hi - w.track_lo;
+    if (nt > 0) CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));   // k_eq's K-weighting epilogue feeds it
     if (!w.eq_n) return AME_OK;
     t_begin(p, S_EQ, s);
-    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_tdev, p->d_luts, d_in, d_pre,
+                                              p->d_energy, p->d_peak);
     LAUNCH_CHECK(p);
     t_end(p, S_EQ, s);
     return AME_OK;
@@ -368,41 +435,30 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
     return AME_OK;
 }
 
-// Threads per chain of k_att_chain_spec (32 speculative time segments per warp), 0 = the queue kernel k_att_chain
-// alone.  Measured on the bench batch (profiles/r01e_summary.md): 2 warps per chain for launches of 192..1152 chains
-// (33.5 ms/step against 40.0 with the queue kernel and 37.4 with 32 segments), 4 warps for the 36-chain waves of the
-// host path (99.6 ms end to end against 107) and for a single track; 8 warps cut the segments so short that the
-// extra repair passes cost more than they save.  The CTA always has two warps or more (in-place fallback).
-int chain_threads(const ame_plan *p, int n_chains) {
-    if (p->chain_warps < 0) return 0;
+// Lanes (time segments) per chain of k_att_chain.  More lanes = shorter segments = cheaper passes but more of them once
+// a segment is shorter than the distance after which trajectories meet; the pass cost is so low on the dense list
+// that 4 warps are right from one track to the full batch, 8 when only a few chains share the machine.
+int chain_lanes(const ame_plan *p, int n_chains) {
+    if (p->chain_warps < 0) return 1;                       // the sequential loop, one lane per chain
     if (p->chain_warps > 0) return 32 * p->chain_warps;
-    const int warps = p->n_sm / std::max(n_chains, 1);
-    return 32 * std::max(2, std::min(warps, 4));
+    return n_chains * 2 <= p->n_sm ? 256 : 128;
 }
 
-int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_pre, cudaStream_t s) {
+int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     if (!w.chain_n) return AME_OK;
     t_begin(p, S_FLAG, s);
-    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, d_bands, p->d_rms, p->mb_frames);
+    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, b.bands, b.rms, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
-    const int ct = chain_threads(p, w.chain_n);
-    if (ct) {
-        // at least two warps, so that a chain that will not settle can be redone in place
-        k_att_chain_spec<<<w.chain_n, std::max(ct, 64), sizeof(ChainSmem), s>>>(p->d_chain_jobs + w.chain_lo, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf,
-                                                                                p->mb_frames, p->d_chain_stuck + w.chain_lo, ct);
-        LAUNCH_CHECK(p);
-    }
-    // the queue kernel: every chain, or (after the speculative kernel) only those it flagged - a CTA without one exits at once
-    k_att_chain<<<(w.chain_n + kChainsPerCta - 1) / kChainsPerCta, kChainsPerCta * 64, kChainsPerCta * sizeof(ChainSmem), s>>>(
-        p->d_chain_jobs + w.chain_lo, w.chain_n, p->d_rms, p->d_tables, p->d_ckpt, p->d_attf, p->mb_frames,
-        ct ? p->d_chain_stuck + w.chain_lo : nullptr);
+    const int lanes = chain_lanes(p, w.chain_n);
+    k_att_chain<<<w.chain_n, std::max(lanes, 128), 0, s>>>(p->d_chain_jobs + w.chain_lo, b.rms, p->d_tables, b.grp, b.att, p->mb_frames,
+                                                           lanes, p->d_chain_stats + 2 * (size_t)w.chain_lo);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);
     t_begin(p, S_APPLY, s);
     k_compress_apply<<<(unsigned)((w.seg_hi - w.seg_lo + 3) / 4), 128, 0, s>>>(p->d_mb_chunks + w.chunk_lo, w.chunk_n, w.seg_lo, w.seg_hi,
-                                                                                d_bands, p->d_rms, p->d_ckpt, p->d_attf, d_pre, p->mb_frames);
+                                                                                b.bands, b.grp, b.att, b.pre, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_APPLY, s);
     return AME_OK;
@@ -411,7 +467,6 @@ int run_compress(ame_plan *p, const Wave &w, const int16_t *d_bands, int16_t *d_
 int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, cudaStream_t s) {
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
-    CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));
     if (w.kw_n) {
         t_begin(p, S_KW, s);
         k_kweight_energy<<<(w.kw_n + 127) / 128, 128, 0, s>>>(p->d_kw_jobs + w.kw_lo, w.kw_n, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
@@ -445,13 +500,25 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
     return AME_OK;
 }
 
-int run_chain_of_stages(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out, cudaStream_t s) {
+int run_measure(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     int rc;
-    if ((rc = run_eq(p, w, d_in, p->d_pre, s))) return rc;
-    if ((rc = run_split(p, w, p->d_pre, p->d_bands, s))) return rc;
-    if ((rc = run_compress(p, w, p->d_bands, p->d_pre, s))) return rc;
-    if ((rc = run_hist(p, w, p->d_pre, (int64_t *)p->d_hist, s))) return rc;
-    return run_gain(p, w, p->d_pre, (const int64_t *)p->d_hist, d_out, s);
+    if ((rc = run_eq(p, w, b.in, b.pre, s))) return rc;
+    if ((rc = run_split(p, w, b.pre, b.bands, s))) return rc;
+    if ((rc = run_compress(p, w, b, s))) return rc;
+    return run_hist(p, w, b.pre, b.hist, s);
+}
+
+int run_chain_of_stages(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
+    int rc = run_measure(p, w, b, s);
+    if (rc) return rc;
+    return run_gain(p, w, b.pre, b.hist, b.out, s);
+}
+
+// after a failure in the middle of a pipelined call nothing may still be reading the caller's buffers when we return
+int drain(ame_plan *p, int rc) {
+    (void)p;
+    if (rc != AME_OK) cudaDeviceSynchronize();
+    return rc;
 }
 
 }  // namespace
@@ -474,16 +541,19 @@ int ame_device_count(int *count) {
 
 void ame_plan_destroy(ame_plan *p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
-                    p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts, p->d_pre, p->d_bands,
-                    p->d_in, p->d_out, p->d_rms, p->d_ckpt, p->d_attf, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results,
-                    p->d_chain_stuck};
+                    p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts,
+                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results,
+                    p->d_chain_stats};
     cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
     for (void *q : ptrs) dev_free(q);
+    for (Slot &sl : p->slots) {
+        for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.grp, (void *)sl.att}) dev_free(q);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     for (cudaStream_t s : {p->s_in, p->s_out})
         if (s) cudaStreamDestroy(s);
-    for (cudaStream_t s : p->s_run) cudaStreamDestroy(s);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_run) cudaEventDestroy(e);
     for (cudaEvent_t e : p->t_ev) cudaEventDestroy(e);
@@ -499,7 +569,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(AME_E_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
-    CU(cudaSetDevice(device));
+    GUARD(device);
     ame_plan_options o{};
     if (opt) o = *opt;
 
@@ -514,7 +584,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     std::vector<std::pair<int64_t, int64_t>> spans;
     p->mb_offset.assign(n_tracks, -1);
     p->tdev.resize(n_tracks);
-    int max_warm_kw = 0, min_s100 = 1 << 30;
+    p->fuse_kw.assign(n_tracks, 0);
     int64_t sum_frames = 0;
     for (int t = 0; t < n_tracks; ++t) {
         ame_track_params &tp = p->tracks[t];
@@ -525,21 +595,22 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         spans.emplace_back(tp.offset_frames, tp.offset_frames + n_total);
         p->total_frames = std::max(p->total_frames, align_up(tp.offset_frames + n_total, 8));
         sum_frames += tp.n_frames;
-        if (tp.flags & AME_F_MULTIBAND) {
-            p->mb_offset[t] = p->mb_frames;
-            p->mb_frames += align_up(n_total, 8);
-        }
         const int s100 = (tp.sample_rate + 5) / 10;
         p->tdev[t].s100 = s100;
         p->tdev[t].n_sb = (int)(n_total / s100);
         p->tdev[t].n_total = n_total;
-        p->tdev[t].pad = 0;
         // blocks whose last sub-block lies in the halo were counted by the previous shard
         p->tdev[t].first_block = tp.halo_frames ? std::max<int>(0, (int)(tp.halo_frames / s100) - 3) : 0;
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
-        max_warm_kw = std::max(max_warm_kw, tp.warm_kw);
-        min_s100 = std::min(min_s100, s100);
+        // K-weighting in the k_eq epilogue: the k_eq output must BE the pre-normalisation signal (no multiband stage,
+        // no halo of another shard in front), tiles and chunks must lie on the 100 ms grid, and the RLB numerator must
+        // be the 1 -2 1 the kernel hard-wires
+        const int64_t cf = tp.chunk_frames;
+        const bool one_chunk = cf <= 0 || tp.n_frames <= cf;
+        p->fuse_kw[t] = o.fuse_kw >= 0 && !(tp.flags & AME_F_MULTIBAND) && tp.halo_frames == 0 && s100 >= 8 &&
+                        (one_chunk || cf % s100 == 0) && tp.kw[1].b0 == 1.0 && tp.kw[1].b1 == -2.0 && tp.kw[1].b2 == 1.0;
+        p->tdev[t].fused = p->fuse_kw[t];
     }
     for (size_t i = 1; i < spans.size(); ++i)
         if (spans[i].first < align_up(spans[i - 1].second, 8)) return bail(fail(AME_E_INVALID, "tracks overlap in the packed buffer"));
@@ -574,10 +645,27 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             wv.frame_hi = (wv.track_hi < n_tracks) ? p->tracks[wv.track_hi].offset_frames : p->total_frames;
         }
     }
+    // Slots: a wave's intermediate buffers (pre-normalisation signal, bands, rms, attenuations) live in slot
+    // w % n_slots and are recycled in stream order, so a batch far larger than the workspace can be planned.
+    int n_slots = o.n_slots > 0 ? o.n_slots : std::min(n_waves, 4);
+    n_slots = std::max(1, std::min(n_slots, n_waves));
+    for (int w = 0; w < n_waves; ++w) {
+        Wave &wv = p->waves[w];
+        wv.slot = w % n_slots;
+        int64_t mb = 0;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t)
+            if (p->tracks[t].flags & AME_F_MULTIBAND) {
+                p->mb_offset[t] = mb;                               // within the wave's own multiband packing
+                mb += align_up(p->tdev[t].n_total, 8);
+            }
+        wv.mb_frames = mb;
+        p->mb_frames = std::max(p->mb_frames, mb);
+        p->slot_frames = std::max(p->slot_frames, wv.frame_hi - wv.frame_lo);
+    }
 
     // ---- chunk geometry, tile sizes -----------------------------------------------------------------
-    // Tiles are sized so that ONE launch fills the machine with one wave of resident threads (no tail wave).
-    // With several plan waves every wave's launch must do so on its own, so the largest wave decides.
+    // Tiles are sized so that ONE launch fills its share of the machine with one wave of resident threads (no tail
+    // wave).  Waves in different slots run concurrently, so a launch gets 1 / min(n_slots, 4) of the resident threads.
     std::vector<std::vector<int64_t>> chunks_all(n_tracks);
     for (int t = 0; t < n_tracks; ++t) {
         const ame_track_params &tp = p->tracks[t];
@@ -590,35 +678,45 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     p->chain_warps = std::max(-1, std::min(o.chain_warps, kChainMaxThreads / 32));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
-    // Waves run on separate streams, so up to ~4 of them share the machine at any time: a wave's launch gets that
-    // share of the resident threads (sizing every wave to fill the machine alone made 16-wave plans do 2.3x the
-    // filter work in warm-up).
-    const int share = std::min(n_waves, 4);
+    const int share = std::min(n_slots, 4);
     const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128 / share;         // one thread per tile
     const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128 / share;
     constexpr int64_t kMinTile = 512;
     int64_t split_tile = kMinTile;
     std::vector<double> eq_cost(n_tracks);
+    std::vector<int64_t> eq_min_tile(n_tracks, kMinTile);
     std::vector<int> eq_warps(n_tracks, 1);
-    for (int t = 0; t < n_tracks; ++t) eq_cost[t] = eq_cost_per_frame(p->tracks[t]);
+    int max_warm_kw = 0, min_s100 = 1 << 30;
+    int64_t n_sb_kw = 0;                                  // sub-blocks left to k_kweight_energy
+    for (int t = 0; t < n_tracks; ++t) {
+        eq_cost[t] = eq_cost_per_frame(p->tracks[t]) + (p->fuse_kw[t] ? kEqCostKw : 0.0);
+        if (p->fuse_kw[t]) eq_min_tile[t] = p->tdev[t].s100;
+        else {
+            n_sb_kw += p->tdev[t].n_sb;
+            max_warm_kw = std::max(max_warm_kw, p->tracks[t].warm_kw);
+            min_s100 = std::min(min_s100, p->tdev[t].s100);
+        }
+    }
     for (const Wave &wv : p->waves) {
         std::vector<int64_t> cm;
         for (int t = wv.track_lo; t < wv.track_hi; ++t)
             if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
         split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
-        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, kMinTile);
+        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, eq_min_tile);
         for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
     }
     p->eq_tile = 0;
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
     if (o.kw_tile_subblocks > 0) {
         p->kw_tile_sb = o.kw_tile_subblocks;
-    } else {
+    } else if (n_sb_kw > 0) {
         // a tile of sub-blocks costs (tile + warm-up) frames: keep the warm-up below ~15 % when the batch is big
         // enough to still give every SM ~512 threads per launch, else shrink the tile towards one sub-block
         const int64_t want = std::max<int64_t>(1, ((int64_t)max_warm_kw * 6 + min_s100 - 1) / min_s100);
-        const int64_t fill = std::max<int64_t>(1, p->n_sb_total / n_waves * share / ((int64_t)n_sm * 512));
+        const int64_t fill = std::max<int64_t>(1, n_sb_kw / n_waves * share / ((int64_t)n_sm * 512));
         p->kw_tile_sb = (int)std::min(want, fill);
+    } else {
+        p->kw_tile_sb = 1;
     }
 
     // ---- job tables (every table is ordered by track, hence contiguous per wave) ---------------------
@@ -637,12 +735,14 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.eq_lo = (int)eq_jobs.size(); wv.split_lo = (int)split_jobs.size(); wv.chain_lo = (int)chain_jobs.size();
         wv.chunk_lo = (int)mb_chunks.size(); wv.kw_lo = (int)kw_jobs.size(); wv.gain_lo = (int)gain_jobs.size();
         wv.seg_lo = n_seg_total;
+        int64_t n_groups = 0;                          // group records of this wave (slot-local indices)
         for (int t = wv.track_lo; t < wv.track_hi; ++t) {
             ame_track_params &tp = p->tracks[t];
             int variant = 0;
             for (int s = 0; s < 4; ++s)
                 if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
             if (tp.flags & AME_F_WARMTH) variant |= 16;
+            if (p->fuse_kw[t]) variant |= 32;
             const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
             if (mb) {
                 mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
@@ -666,22 +766,25 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             {
                 int64_t c0e = 0;
                 const int64_t want = (int64_t)eq_warps[t] * 32;
+                const int64_t q = p->fuse_kw[t] ? p->tdev[t].s100 : 8;
                 for (int64_t cn : chunks_all[t]) {
                     const int64_t cb = tp.offset_frames + tp.halo_frames + c0e, ce = cb + cn;
                     int64_t T;
                     if (o.eq_tile_frames > 0) {
-                        T = align_up(o.eq_tile_frames, 8);
+                        T = align_up(o.eq_tile_frames, q);
                     } else {
                         const int64_t jc = std::max<int64_t>(1, want * cn / std::max<int64_t>(tp.n_frames, 1));   // floor: never over `want`
-                        T = std::max<int64_t>(kMinTile, align_up((cn + jc - 1) / jc, 8));
+                        T = std::max<int64_t>(eq_min_tile[t], align_up((cn + jc - 1) / jc, q));
                     }
-                    tile_jobs(eq_jobs, t, variant, cb, ce, T);
-                    p->eq_tile = std::max<int>(p->eq_tile, (int)T);
+                    if (p->fuse_kw[t]) tile_jobs_grid(eq_jobs, t, variant, cb, ce, T, q);
+                    else tile_jobs(eq_jobs, t, variant, cb, ce, T);
+                    p->eq_tile = std::max<int>(p->eq_tile, (int)std::min<int64_t>(T, INT32_MAX));
                     c0e += cn;
                 }
                 if (eq_jobs.size() > eq_first) {            // whole warps per track: pad with empty jobs
                     TileJob d = eq_jobs.back();
                     d.tile_begin = d.tile_end;
+                    d.variant &= ~32;                       // an empty job has nothing to measure
                     while ((eq_jobs.size() - eq_first) % 32) eq_jobs.push_back(d);
                 }
             }
@@ -694,22 +797,25 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                     for (int b = 0; b < 3; ++b) {
                         const double thr = tp.comp[b].thresh_rms;
                         const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
-                        ck.ck_begin[b] = p->n_group_total;
-                        chain_jobs.push_back(ChainJob{ck.mb_begin, cn, p->n_group_total, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
-                        p->n_group_total += (cn + 31) / 32;
+                        ck.grp_begin[b] = n_groups;
+                        chain_jobs.push_back(ChainJob{ck.mb_begin, cn, n_groups, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
+                        n_groups += (cn + 31) / 32;
                     }
                     n_seg_total += (cn + kSeg - 1) / kSeg;
                     mb_chunks.push_back(ck);
                 }
                 c0 += cn;
             }
-            for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
-                kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
+            if (!p->fuse_kw[t])
+                for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
+                    kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
             for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
                 gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
                                             tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
         }
-        // longest chains first inside the wave: the sequential kernel is bounded by its slowest warp
+        wv.n_groups = n_groups;
+        p->slot_groups = std::max(p->slot_groups, n_groups);
+        // longest chains first inside the wave: the launch ends with its slowest CTA
         std::stable_sort(chain_jobs.begin() + wv.chain_lo, chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
         wv.wf_lo = (int)wf_jobs.size();
         for (int c = wv.chain_lo; c < (int)chain_jobs.size(); ++c)
@@ -719,15 +825,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
         wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
     }
-    p->all = p->waves.front();
-    {
-        const Wave &l = p->waves.back();
-        Wave &a = p->all;
-        a.track_hi = l.track_hi; a.frame_hi = l.frame_hi;
-        a.eq_n = l.eq_lo + l.eq_n; a.split_n = l.split_lo + l.split_n; a.chain_n = l.chain_lo + l.chain_n;
-        a.wf_n = l.wf_lo + l.wf_n; a.chunk_n = l.chunk_lo + l.chunk_n; a.kw_n = l.kw_lo + l.kw_n;
-        a.gain_n = l.gain_lo + l.gain_n; a.seg_hi = l.seg_hi;
-    }
 
     // ---- device state -------------------------------------------------------------------------
     if ((rc = upload(&p->d_tracks, p->tracks)) || (rc = upload(&p->d_tdev, p->tdev)) || (rc = upload(&p->d_mb_delta, mb_delta)) ||
@@ -736,19 +833,34 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         (rc = upload(&p->d_kw_jobs, kw_jobs)) || (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_tables, tables)))
         return bail(rc);
     const size_t fb = (size_t)p->total_frames * 4;
-    if ((rc = dmalloc(p, (void **)&p->d_pre, fb)) || (rc = dmalloc(p, (void **)&p->d_bands, (size_t)p->mb_frames * 4 * 3)) ||
-        (rc = dmalloc(p, (void **)&p->d_rms, (size_t)p->mb_frames * 2 * 3)) ||
-        (rc = dmalloc(p, (void **)&p->d_ckpt, (size_t)p->n_group_total * 8)) ||
-        (rc = dmalloc(p, (void **)&p->d_chain_stuck, chain_jobs.size() * sizeof(int))) ||
-        (rc = dmalloc(p, (void **)&p->d_attf, (size_t)p->mb_frames * 8 * 3)) ||
+    p->slots.resize(n_slots);
+    for (Slot &sl : p->slots) {
+        if ((rc = dmalloc(p, (void **)&sl.pre, (size_t)p->slot_frames * 4)) ||
+            (rc = dmalloc(p, (void **)&sl.bands, (size_t)p->mb_frames * 4 * 3)) ||
+            (rc = dmalloc(p, (void **)&sl.rms, (size_t)p->mb_frames * 2 * 3)) ||
+            (rc = dmalloc(p, (void **)&sl.grp, (size_t)p->slot_groups * sizeof(GrpRec))) ||
+            (rc = dmalloc(p, (void **)&sl.att, (size_t)p->mb_frames * 8 * 3)))
+            return bail(rc);
+        // the filters read a few frames past a track's end (whole 16 / 32-byte groups, never stored): keep them defined
+        if (cudaMemsetAsync(sl.pre, 0, (size_t)p->slot_frames * 4, 0) != cudaSuccess ||
+            (p->mb_frames && cudaMemsetAsync(sl.bands, 0, (size_t)p->mb_frames * 12, 0) != cudaSuccess))
+            return bail(fail(AME_E_CUDA, "cudaMemset failed"));
+    }
+    if ((rc = dmalloc(p, (void **)&p->d_chain_stats, std::max<size_t>(chain_jobs.size(), 1) * 2 * sizeof(int))) ||
         (rc = dmalloc(p, (void **)&p->d_energy, (size_t)std::max<int64_t>(p->n_sb_total, 1) * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist_st, (size_t)n_tracks * 1000 * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_results, (size_t)n_tracks * sizeof(ame_track_result))))
         return bail(rc);
+    if (cudaMemsetAsync(p->d_chain_stats, 0, std::max<size_t>(chain_jobs.size(), 1) * 2 * sizeof(int), 0) != cudaSuccess)
+        return bail(fail(AME_E_CUDA, "cudaMemset failed"));
     if (o.host_io) {
         if ((rc = dmalloc(p, (void **)&p->d_in, fb)) || (rc = dmalloc(p, (void **)&p->d_out, fb))) return bail(rc);
+        // pool memory is recycled: the padding between tracks is copied back to the caller with the wave, so it must
+        // not carry another plan's audio
+        if (cudaMemsetAsync(p->d_in, 0, fb, 0) != cudaSuccess || cudaMemsetAsync(p->d_out, 0, fb, 0) != cudaSuccess)
+            return bail(fail(AME_E_CUDA, "cudaMemset failed"));
         if (cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaStreamCreate failed"));
@@ -756,26 +868,14 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     if (o.host_io || n_waves > 1) {
         p->ev_in.resize(n_waves);
         p->ev_run.resize(n_waves);
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically lower = higher priority
-        for (int w = 0; w < n_waves; ++w) {
-            // earlier waves get the higher priority so a wave that is ahead in the pipeline is never starved by
-            // the bulk kernels of the waves behind it
-            cudaStream_t st = nullptr;
-            const int prio = std::max(prio_hi, std::min(prio_lo, prio_hi + w));
-            if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess)
+        for (Slot &sl : p->slots)
+            if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess)
                 return bail(fail(AME_E_CUDA, "cudaStreamCreate failed"));
-            p->s_run.push_back(st);
+        for (int w = 0; w < n_waves; ++w)
             if (cudaEventCreateWithFlags(&p->ev_in[w], cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&p->ev_run[w], cudaEventDisableTiming) != cudaSuccess)
                 return bail(fail(AME_E_CUDA, "cudaEventCreate failed"));
-        }
     }
-    if (cudaMemset(p->d_pre, 0, fb) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
-    if (p->mb_frames && cudaMemset(p->d_bands, 0, (size_t)p->mb_frames * 12) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
-
-    if (cudaFuncSetAttribute(k_att_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChainsPerCta * sizeof(ChainSmem))) != cudaSuccess)
-        return bail(fail(AME_E_CUDA, "cannot reserve %zu bytes of shared memory for k_att_chain", kChainsPerCta * sizeof(ChainSmem)));
 
     // ebur128.c histogram tables (same libm calls as the C library)
     {
@@ -787,13 +887,15 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             cudaMemcpyToSymbol(c_hist_energy, energies, sizeof energies) != cudaSuccess)
             return bail(fail(AME_E_CUDA, "cudaMemcpyToSymbol failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
-    CU(cudaStreamSynchronize(0));       // allocations are ordered on the default stream; the plan runs on others
+    // allocations and clears are ordered on the default stream; the plan runs on others
+    if (cudaError_t e = cudaStreamSynchronize(0); e != cudaSuccess)
+        return bail(fail(AME_E_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e)));
     *out = p;
     return AME_OK;
 }
 
 int ame_release_cached_memory(int device) {
-    CU(cudaSetDevice(device));
+    GUARD(device);
     CU(cudaDeviceSynchronize());
     if (cudaMemPool_t pool = device_pool()) CU(cudaMemPoolTrimTo(pool, 0));
     return AME_OK;
@@ -801,8 +903,14 @@ int ame_release_cached_memory(int device) {
 
 int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
     if (!p || !luts || n_luts <= 0) return fail(AME_E_INVALID, "bad warm lut arguments");
-    CU(cudaSetDevice(p->device));
-    if (p->d_luts) { CU(cudaDeviceSynchronize()); dev_free(p->d_luts); p->d_luts = nullptr; }
+    GUARD(p->device);
+    if (p->d_luts) {
+        CU(cudaDeviceSynchronize());
+        dev_free(p->d_luts);
+        p->d_luts = nullptr;
+        p->ws_bytes -= (size_t)p->n_luts * 65536 * sizeof(double);
+        p->n_luts = 0;
+    }
     // widened exactly to double on the host so the kernel needs no float->double conversion per sample
     std::vector<double> wide((size_t)n_luts * 65536);
     for (size_t i = 0; i < wide.size(); ++i) wide[i] = (double)luts[i];
@@ -818,24 +926,47 @@ int64_t ame_plan_total_frames(const ame_plan *p) { return p ? p->total_frames : 
 size_t ame_plan_workspace_bytes(const ame_plan *p) { return p ? p->ws_bytes : 0; }
 int64_t ame_plan_launch_count(const ame_plan *p) { return p ? p->launches : 0; }
 int32_t ame_plan_wave_count(const ame_plan *p) { return p ? (int32_t)p->waves.size() : 0; }
-const int16_t *ame_plan_tap_pre(const ame_plan *p) { return p->d_pre; }
-const int16_t *ame_plan_tap_bands(const ame_plan *p) { return p->d_bands; }
-const double *ame_plan_tap_subblock_energy(const ame_plan *p) { return p->d_energy; }
-int64_t ame_plan_mb_frames(const ame_plan *p) { return p->mb_frames; }
-int64_t ame_plan_mb_offset(const ame_plan *p, int32_t t) { return (t < 0 || t >= p->n_tracks) ? -1 : p->mb_offset[t]; }
-int64_t ame_plan_subblock_offset(const ame_plan *p, int32_t t) { return (t < 0 || t >= p->n_tracks) ? -1 : p->tdev[t].sb_offset; }
+int32_t ame_plan_slot_count(const ame_plan *p) { return p ? (int32_t)p->slots.size() : 0; }
+const int16_t *ame_plan_tap_pre(const ame_plan *p) { return (p && p->waves.size() == 1) ? p->slots[0].pre : nullptr; }
+const int16_t *ame_plan_tap_bands(const ame_plan *p) { return (p && p->waves.size() == 1) ? p->slots[0].bands : nullptr; }
+const double *ame_plan_tap_subblock_energy(const ame_plan *p) { return p ? p->d_energy : nullptr; }
+int64_t ame_plan_mb_frames(const ame_plan *p) { return p ? p->mb_frames : 0; }
+int64_t ame_plan_mb_offset(const ame_plan *p, int32_t t) { return (!p || t < 0 || t >= p->n_tracks) ? -1 : p->mb_offset[t]; }
+int64_t ame_plan_subblock_offset(const ame_plan *p, int32_t t) { return (!p || t < 0 || t >= p->n_tracks) ? -1 : p->tdev[t].sb_offset; }
 
 int ame_plan_read_device(ame_plan *p, void *h_dst, const void *d_src, size_t bytes) {
     if (!p || !h_dst || !d_src) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    GUARD(p->device);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return AME_OK;
 }
 
+int ame_plan_chain_stats(ame_plan *p, int64_t *n_chains, int64_t *steps, int64_t *max_steps, int64_t *passes, int32_t *max_passes) {
+    if (!p) return fail(AME_E_INVALID, "NULL plan");
+    GUARD(p->device);
+    CU(cudaDeviceSynchronize());
+    int64_t nc = 0;
+    for (const Wave &w : p->waves) nc += w.chain_n;
+    std::vector<int> h((size_t)std::max<int64_t>(nc, 1) * 2, 0);
+    if (nc) CU(cudaMemcpy(h.data(), p->d_chain_stats, (size_t)nc * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    int64_t st = 0, mx = 0, ps = 0;
+    int mp = 0;
+    for (int64_t c = 0; c < nc; ++c) {
+        st += h[2 * c]; mx = std::max<int64_t>(mx, h[2 * c]);
+        ps += h[2 * c + 1]; mp = std::max(mp, h[2 * c + 1]);
+    }
+    if (n_chains) *n_chains = nc;
+    if (steps) *steps = st;
+    if (max_steps) *max_steps = mx;
+    if (passes) *passes = ps;
+    if (max_passes) *max_passes = mp;
+    return AME_OK;
+}
+
 int ame_plan_set_timing(ame_plan *p, int enable) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
-    CU(cudaSetDevice(p->device));
+    GUARD(p->device);
     if (enable && p->t_ev.empty()) {
         p->t_ev.resize((size_t)kMaxTimedSteps * kTimedSlots * 2);
         for (auto &e : p->t_ev) CU(cudaEventCreate(&e));
@@ -848,7 +979,7 @@ int ame_plan_set_timing(ame_plan *p, int enable) {
 
 int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n_steps) {
     if (!p || !ms_sum || !launches) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    GUARD(p->device);
     CU(cudaDeviceSynchronize());
     const int steps = std::min(p->t_step + 1, kMaxTimedSteps);
     for (int k = 0; k < AME_N_KERNELS; ++k) { ms_sum[k] = 0; launches[k] = 0; }
@@ -865,7 +996,7 @@ int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n
 
 int ame_plan_wave_timeline(ame_plan *p, float *ms, int max_waves) {
     if (!p || !ms) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    GUARD(p->device);
     CU(cudaDeviceSynchronize());
     const int n = std::min(p->tl_waves, max_waves);
     for (int w = 0; w < n; ++w)
@@ -873,41 +1004,52 @@ int ame_plan_wave_timeline(ame_plan *p, float *ms, int max_waves) {
     return n;
 }
 
-// ---- stage entry points (one launch over the whole batch) ------------------------------------------
+// ---- stage entry points (one launch over the whole batch; plans with ONE wave) ----------------------
+#define SINGLE_WAVE(p)                                                                             \
+    if ((p)->waves.size() != 1) return fail(AME_E_INVALID, "the stage entry points need a plan with one wave (n_waves <= 1)")
+
 int ame_stage_eq(ame_plan *p, const int16_t *d_in, int16_t *d_pre, void *stream) {
     if (!p || !d_in || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    SINGLE_WAVE(p);
+    GUARD(p->device);
     int rc = check_warmth(p);
     if (rc) return rc;
-    return run_eq(p, p->all, d_in, d_pre, (cudaStream_t)stream);
+    return run_eq(p, p->waves[0], d_in, d_pre, (cudaStream_t)stream);
 }
 
 int ame_stage_band_split(ame_plan *p, const int16_t *d_pre, int16_t *d_bands, void *stream) {
     if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    if (p->all.split_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-    return run_split(p, p->all, d_pre, d_bands, (cudaStream_t)stream);
+    SINGLE_WAVE(p);
+    GUARD(p->device);
+    if (p->waves[0].split_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
+    return run_split(p, p->waves[0], d_pre, d_bands, (cudaStream_t)stream);
 }
 
 int ame_stage_compress(ame_plan *p, int16_t *d_bands, int16_t *d_pre, void *stream) {
     if (!p || !d_pre) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    if (p->all.chain_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
-    return run_compress(p, p->all, d_bands, d_pre, (cudaStream_t)stream);
+    SINGLE_WAVE(p);
+    GUARD(p->device);
+    if (p->waves[0].chain_n && !d_bands) return fail(AME_E_INVALID, "NULL bands buffer");
+    Bufs b = slot_bufs(p, p->waves[0], nullptr, nullptr);
+    b.bands = d_bands;
+    b.pre = d_pre;
+    return run_compress(p, p->waves[0], b, (cudaStream_t)stream);
 }
 
 int ame_stage_loudness_hist(ame_plan *p, const int16_t *d_pre, int64_t *d_hist, void *stream) {
     if (!p || !d_pre || !d_hist) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
-    return run_hist(p, p->all, d_pre, d_hist, (cudaStream_t)stream);
+    SINGLE_WAVE(p);
+    GUARD(p->device);
+    return run_hist(p, p->waves[0], d_pre, d_hist, (cudaStream_t)stream);
 }
 
 int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out,
                          ame_track_result *results, void *stream) {
     if (!p || !d_pre || !d_hist || !d_out) return fail(AME_E_INVALID, "NULL argument");
-    CU(cudaSetDevice(p->device));
+    SINGLE_WAVE(p);
+    GUARD(p->device);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = run_gain(p, p->all, d_pre, d_hist, d_out, s);
+    int rc = run_gain(p, p->waves[0], d_pre, d_hist, d_out, s);
     if (rc) return rc;
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
@@ -916,47 +1058,71 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
     return AME_OK;
 }
 
+// two-phase form: every wave must keep its pre-normalisation signal between the two calls (n_slots == n_waves)
 int ame_measure_device(ame_plan *p, const int16_t *d_in, int64_t *d_hist, void *stream) {
-    if (!p) return fail(AME_E_INVALID, "NULL plan");
+    if (!p || !d_in || !d_hist) return fail(AME_E_INVALID, "NULL argument");
+    if (p->slots.size() != p->waves.size()) return fail(AME_E_INVALID, "the two-phase calls need n_slots == n_waves");
+    GUARD(p->device);
+    int rc = check_warmth(p);
+    if (rc) return rc;
     p->launches = 0;
-    p->t_wave = 0;
     if (p->timing) ++p->t_step;
-    int rc;
-    if ((rc = ame_stage_eq(p, d_in, p->d_pre, stream))) return rc;
-    if ((rc = ame_stage_band_split(p, p->d_pre, p->d_bands, stream))) return rc;
-    if ((rc = ame_stage_compress(p, p->d_bands, p->d_pre, stream))) return rc;
-    return ame_stage_loudness_hist(p, p->d_pre, d_hist, stream);
+    for (size_t w = 0; w < p->waves.size(); ++w) {
+        p->t_wave = (int)std::min<size_t>(w, kMaxTimedWaves - 1);
+        Bufs b = slot_bufs(p, p->waves[w], d_in, nullptr);
+        b.hist = d_hist;
+        if ((rc = run_measure(p, p->waves[w], b, (cudaStream_t)stream))) return rc;
+    }
+    return AME_OK;
 }
 
 int ame_normalize_device(ame_plan *p, const int64_t *d_hist, int16_t *d_out, ame_track_result *results, void *stream) {
-    if (!p) return fail(AME_E_INVALID, "NULL plan");
-    return ame_stage_apply_gain(p, p->d_pre, d_hist, d_out, results, stream);
+    if (!p || !d_hist || !d_out) return fail(AME_E_INVALID, "NULL argument");
+    if (p->slots.size() != p->waves.size()) return fail(AME_E_INVALID, "the two-phase calls need n_slots == n_waves");
+    GUARD(p->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    for (size_t w = 0; w < p->waves.size(); ++w) {
+        p->t_wave = (int)std::min<size_t>(w, kMaxTimedWaves - 1);
+        const Bufs b = slot_bufs(p, p->waves[w], nullptr, d_out);
+        if ((rc = run_gain(p, p->waves[w], b.pre, d_hist, d_out, s))) return rc;
+    }
+    if (results) {
+        CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return AME_OK;
 }
 
 int ame_master_device(ame_plan *p, const int16_t *d_in, int16_t *d_out, ame_track_result *results, void *stream) {
     if (!p) return fail(AME_E_INVALID, "NULL plan");
     if (!d_in || !d_out) return fail(AME_E_INVALID, "NULL argument");
-    const int nw = (int)p->waves.size();
-    if (nw <= 1) {
-        int rc = ame_measure_device(p, d_in, (int64_t *)p->d_hist, stream);
-        if (rc) return rc;
-        return ame_normalize_device(p, (const int64_t *)p->d_hist, d_out, results, stream);
-    }
-    // several waves: fork the caller's stream into one stream per wave and join again, so the latency-bound
-    // sequential compressor kernel of one wave overlaps the bulk kernels of the others
-    CU(cudaSetDevice(p->device));
+    GUARD(p->device);
     int rc = check_warmth(p);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    const int nw = (int)p->waves.size();
     p->launches = 0;
     if (p->timing) ++p->t_step;
-    CU(cudaEventRecord(p->ev_in[0], s));
-    for (int w = 0; w < nw; ++w) {
-        CU(cudaStreamWaitEvent(p->s_run[w], p->ev_in[0], 0));
-        p->t_wave = w;
-        if ((rc = run_chain_of_stages(p, p->waves[w], d_in, d_out, p->s_run[w]))) return rc;
-        CU(cudaEventRecord(p->ev_run[w], p->s_run[w]));
-        CU(cudaStreamWaitEvent(s, p->ev_run[w], 0));
+    if (nw <= 1) {
+        p->t_wave = 0;
+        if ((rc = run_chain_of_stages(p, p->waves[0], slot_bufs(p, p->waves[0], d_in, d_out), s))) return rc;
+    } else {
+        // several waves: fork the caller's stream into the slots' streams and join again.  Waves of different slots
+        // overlap (the latency-bound compressor kernels of one under the FP64-bound filters of another); waves of
+        // one slot follow each other in stream order, which is what recycles the slot.
+        CU(cudaEventRecord(p->ev_in[0], s));
+        const int ns = (int)p->slots.size();
+        for (int w = 0; w < nw; ++w) {
+            cudaStream_t ws = p->slots[p->waves[w].slot].stream;
+            if (w < ns) CU(cudaStreamWaitEvent(ws, p->ev_in[0], 0));
+            p->t_wave = std::min(w, kMaxTimedWaves - 1);
+            if ((rc = run_chain_of_stages(p, p->waves[w], slot_bufs(p, p->waves[w], d_in, d_out), ws))) return drain(p, rc);
+        }
+        for (int k = 0; k < ns; ++k) {
+            CU(cudaEventRecord(p->ev_run[k], p->slots[k].stream));
+            CU(cudaStreamWaitEvent(s, p->ev_run[k], 0));
+        }
     }
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
@@ -965,14 +1131,10 @@ int ame_master_device(ame_plan *p, const int16_t *d_in, int16_t *d_out, ame_trac
     return AME_OK;
 }
 
-// Host buffers: wave w's H2D copy (stream s_in), kernels (its own stream) and D2H copy (s_out) are chained by
-// events, so the copy engines (PCIe is full duplex) and the SMs work on different waves at the same time, and
-// the latency-bound sequential kernel of one wave overlaps the bulk kernels of the others.  Pinned host memory
-// makes the copies truly asynchronous; pageable memory still works, the copies then serialise.
-int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_result *results) {
-    if (!p || !h_in || !h_out) return fail(AME_E_INVALID, "NULL argument");
-    if (!p->d_in || !p->d_out) return fail(AME_E_INVALID, "plan was created without host_io");
-    CU(cudaSetDevice(p->device));
+// Host buffers: wave w's H2D copy (stream s_in), kernels (its slot's stream) and D2H copy (s_out) are chained by
+// events, so the copy engines (PCIe is full duplex) and the SMs work on different waves at the same time.  Pinned host
+// memory makes the copies truly asynchronous; pageable memory still works, the copies then serialise.
+static int master_host_impl(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_result *results) {
     int rc = check_warmth(p);
     if (rc) return rc;
     p->launches = 0;
@@ -996,12 +1158,13 @@ int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_
         if (tl) CU(cudaEventRecord(p->tl_ev[1 + 4 * w], p->s_in));
     }
     for (int w = 0; w < nw; ++w) {
-        CU(cudaStreamWaitEvent(p->s_run[w], p->ev_in[w], 0));
-        if (tl) CU(cudaEventRecord(p->tl_ev[2 + 4 * w], p->s_run[w]));
-        p->t_wave = w;
-        if ((rc = run_chain_of_stages(p, p->waves[w], p->d_in, p->d_out, p->s_run[w]))) return rc;
-        CU(cudaEventRecord(p->ev_run[w], p->s_run[w]));
-        if (tl) CU(cudaEventRecord(p->tl_ev[3 + 4 * w], p->s_run[w]));
+        cudaStream_t ws = p->slots[p->waves[w].slot].stream;
+        CU(cudaStreamWaitEvent(ws, p->ev_in[w], 0));
+        if (tl) CU(cudaEventRecord(p->tl_ev[2 + 4 * w], ws));
+        p->t_wave = std::min(w, kMaxTimedWaves - 1);
+        if ((rc = run_chain_of_stages(p, p->waves[w], slot_bufs(p, p->waves[w], p->d_in, p->d_out), ws))) return rc;
+        CU(cudaEventRecord(p->ev_run[w], ws));
+        if (tl) CU(cudaEventRecord(p->tl_ev[3 + 4 * w], ws));
     }
     for (int w = 0; w < nw; ++w) {
         const Wave &wv = p->waves[w];
@@ -1014,6 +1177,14 @@ int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, p->s_out));
     CU(cudaStreamSynchronize(p->s_out));
     return AME_OK;
+}
+
+int ame_master_host(ame_plan *p, const int16_t *h_in, int16_t *h_out, ame_track_result *results) {
+    if (!p || !h_in || !h_out) return fail(AME_E_INVALID, "NULL argument");
+    if (!p->d_in || !p->d_out) return fail(AME_E_INVALID, "plan was created without host_io");
+    GUARD(p->device);
+    // whatever fails in the middle: no copy or kernel may still touch h_in / h_out once we have returned
+    return drain(p, master_host_impl(p, h_in, h_out, results));
 }
 
 }  // extern "C"

@@ -30,7 +30,7 @@ struct TileJob {           // one lane pair of k_eq / k_band_split
 struct ChainJob {          // one warp of k_compress: one band of one chunk of a multiband track
     int64_t mb_begin;      // of the chunk, in the multiband-only packing (bands planes)
     int64_t n;             // frames
-    int64_t ck_begin;      // first slot of this chain in the per-group checkpoint array
+    int64_t grp_begin;     // first slot of this chain in the per-group record array
     int32_t band;
     int32_t table;
     uint32_t thr_i;        // rms > thresh_rms  <=>  rms >= thr_i
@@ -50,7 +50,7 @@ struct TrackDev {          // device-side per-track bookkeeping
     int32_t n_sb;          // number of complete 100 ms sub-blocks (halo included)
     int32_t s100;          // frames per 100 ms = (fs + 5) / 10   (ebur128.c)
     int32_t first_block;   // time shards: 400 ms blocks before this one belong to the previous shard / the warm-up
-    int32_t pad;
+    int32_t fused;         // K-weighting runs in the k_eq epilogue (no k_kweight_energy jobs)
     int64_t n_total;       // halo + span frames
 };
 
@@ -65,6 +65,13 @@ __device__ __forceinline__ double bq_step(const ame_biquad &c, double &z0, doubl
     double y = fma(c.b0, x, z0);
     z0 = fma(-c.a1, y, fma(c.b1, x, z1));
     z1 = fma(-c.a2, y, c.b2 * x);
+    return y;
+}
+
+__device__ __forceinline__ double kw_pre(double b0, double b1, double b2, double a1, double a2, double &z0, double &z1, double x) {
+    const double y = fma(b0, x, z0);                       // == bq_step on the same coefficients
+    z0 = fma(-a1, y, fma(b1, x, z1));
+    z1 = fma(-a2, y, b2 * x);
     return y;
 }
 
@@ -107,6 +114,15 @@ __device__ __forceinline__ double bw_step1(double a1, double a2, double &z0, dou
     return y;
 }
 
+// apply_shelf_filter with a negative gain (:289): samples * g + (y - samples * g), i.e. y up to one rounding.  When the
+// stage is the first active one its input is still the float32 channel, and numpy evaluates samples * g in float32
+// (a Python float does not widen a float32 array); later stages see float64.  No FMA contraction.
+template <bool FIRST>
+__device__ __forceinline__ double shelf_cut(double v, double f, double g) {
+    const double t = FIRST ? (double)__fmul_rn((float)v, (float)g) : __dmul_rn(v, g);
+    return __dadd_rn(t, __dsub_rn(f, t));
+}
+
 struct PeakCoef { double b0, a1[4], a2[4]; };     // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
 __device__ __forceinline__ void load_peak(PeakCoef &c, const ame_eq_stage &st) {
     c.b0 = st.s[0].b0;
@@ -127,14 +143,19 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 
 // ------------------------------------------------------------------------------------------------
 // k_eq: int16 in -> [warmth -> int16] -> float32 -> 4-stage EQ in FP64 -> float32 -> [width] -> int16
+//       [-> K-weighting -> 100 ms energies + sample peak, for tracks without a multiband stage]
 // ONE THREAD per tile, both channels: the L and R cascades are two independent dependency chains in one
 // instruction stream (the kernel is bound by FP64 latency, not by registers), and the cross-channel
 // stages (warmth, width, packing) need no shuffles.  MASK = active EQ stages, WARM = warmth on.
+// KW = the K-weighting of the loudness measurement runs in the epilogue on the int16 value just produced (it IS the
+// pre-normalisation signal when the track has no multiband stage), so that signal is not read again: tiles then lie
+// on the track's 100 ms sub-block grid, the warm-up grows by the K filter's, and since the K filter runs through the
+// whole track while the EQ restarts with every chunk, the EQ state is reset when the walk crosses a chunk start.
 // ------------------------------------------------------------------------------------------------
-template <int MASK, bool WARM>
-__device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
+template <int MASK, bool WARM, bool KW>
+__device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp, const TrackDev *__restrict__ tdp,
                                         const double *__restrict__ luts, const int16_t *__restrict__ in,
-                                        int16_t *__restrict__ pre) {
+                                        int16_t *__restrict__ pre, double *__restrict__ energy, int *__restrict__ peak) {
     const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
     const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
@@ -160,10 +181,33 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
 #pragma unroll
     for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
 
-    const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
-    int64_t f_lo = job.tile_begin - warm;
-    if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
     const int64_t f_hi = job.tile_end;
+    int64_t f_lo, zero_before, next_reset = INT64_MAX;
+    const int64_t cf = tp->chunk_frames > 0 ? (int64_t)tp->chunk_frames : INT64_MAX / 4;
+    // K-weighting state (BS.1770 pre-filter: general biquad; RLB high-pass: numerator exactly 1 -2 1)
+    double k0b0 = 0, k0b1 = 0, k0b2 = 0, k0a1 = 0, k0a2 = 0, k1a1 = 0, k1a2 = 0;
+    double kzl[4] = {0, 0, 0, 0}, kzr[4] = {0, 0, 0, 0}, accl = 0, accr = 0;
+    int pk = 0, sb = 0, n_sb = 0, s100 = 1, left = 1;
+    int64_t sb_off = 0;
+    if (KW) {
+        const int64_t track_begin = tp->offset_frames;     // no halo on tracks that take this path
+        const int64_t warm = ((MASK != 0) ? (int64_t)tp->warm_eq : 0) + (int64_t)tp->warm_kw;
+        f_lo = job.tile_begin - warm;
+        if (f_lo < track_begin) f_lo = track_begin;
+        zero_before = track_begin;
+        next_reset = track_begin + ((f_lo - track_begin) / cf + 1) * cf;     // first chunk start after f_lo
+        k0b0 = tp->kw[0].b0; k0b1 = tp->kw[0].b1; k0b2 = tp->kw[0].b2; k0a1 = tp->kw[0].a1; k0a2 = tp->kw[0].a2;
+        k1a1 = tp->kw[1].a1; k1a2 = tp->kw[1].a2;
+        const TrackDev td = *tdp;
+        s100 = td.s100; n_sb = td.n_sb; sb_off = td.sb_offset;
+        sb = (int)((job.tile_begin - track_begin) / s100);  // tiles of this path start on the sub-block grid
+        left = s100;
+    } else {
+        const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
+        f_lo = job.tile_begin - warm;
+        if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
+        zero_before = job.chunk_begin;
+    }
     if (f_hi <= f_lo) return;
     const int64_t g0f = f_lo & ~(int64_t)3;               // first 4-aligned group
     const int n_it = (int)((f_hi - g0f + 3) >> 2);
@@ -171,20 +215,25 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     auto cascade = [&](double v, double *z) -> float {     // one channel through the 4 EQ stages
         if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
             const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
-            v = boost0 ? v + (f - v) * gm0 : v * g0 + (f - v * g0);
+            v = boost0 ? v + (f - v) * gm0 : shelf_cut<true>(v, f, g0);
         }
         if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
         if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
         if (MASK & 8) {   // apply_shelf_filter 8 kHz high
             const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
-            v = boost3 ? v + (f - v) * gm3 : v * g3 + (f - v * g3);
+            v = boost3 ? v + (f - v) * gm3 : shelf_cut<(MASK & 7) == 0>(v, f, g3);
         }
         return __double2float_rn(v);                       // samples[:, i] = ... into the float32 array (:274)
     };
 
     // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
-    auto frame = [&](uint32_t w, double lutL, double lutR) -> uint32_t {
+    auto frame = [&](uint32_t w, double lutL, double lutR, int64_t f) -> uint32_t {
         int xl = (int)(int16_t)(w & 0xffffu), xr = (int)(int16_t)(w >> 16);
+        if (KW && f == next_reset) {                       // a chunk starts here: the reference restarts the EQ (:185-199)
+#pragma unroll
+            for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
+            next_reset += cf;
+        }
         if (WARM) {
             // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh, widened
             // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels:
@@ -216,16 +265,33 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
             yl = __fadd_rn(mid, side);
             yr = __fsub_rn(mid, side);
         }
-        return pack16(to_pcm_f32(yl), to_pcm_f32(yr));     // clip inside to_pcm == np.clip of (:270) then (:255)
+        const int ol = to_pcm_f32(yl), orr = to_pcm_f32(yr);   // clip inside to_pcm == np.clip of (:270) then (:255)
+        if (KW) {
+            // ebur128 filter on x / 32768 (k_kweight_energy has the same arithmetic); energies only inside the tile
+            const double kl = bw_step1<-1>(k1a1, k1a2, kzl[2], kzl[3], kw_pre(k0b0, k0b1, k0b2, k0a1, k0a2, kzl[0], kzl[1], i16_to_unit(ol)));
+            const double kr = bw_step1<-1>(k1a1, k1a2, kzr[2], kzr[3], kw_pre(k0b0, k0b1, k0b2, k0a1, k0a2, kzr[0], kzr[1], i16_to_unit(orr)));
+            if (f >= job.tile_begin && f < f_hi) {
+                pk = max(pk, max(abs(ol), abs(orr)));
+                if (sb < n_sb) {
+                    accl = fma(kl, kl, accl);
+                    accr = fma(kr, kr, accr);
+                    if (--left == 0) {
+                        energy[sb_off + sb] = accl + accr;   // ebur128: per-channel sums, then added
+                        accl = 0; accr = 0; ++sb; left = s100;
+                    }
+                }
+            }
+        }
+        return pack16(ol, orr);
     };
 
     const uint4 *src = reinterpret_cast<const uint4 *>(in) + (g0f >> 2);
     uint4 *dst = reinterpret_cast<uint4 *>(pre) + (g0f >> 2);
     // software pipeline: input words two groups ahead, tanh-table values one group ahead
     uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
-    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // frames before the chunk start keep the zero state
-    if (g0f + 1 < job.chunk_begin) cur.y = 0;
-    if (g0f + 2 < job.chunk_begin) cur.z = 0;
+    if (g0f + 0 < zero_before) cur.x = 0;                  // frames before the chunk (track) start keep the zero state
+    if (g0f + 1 < zero_before) cur.y = 0;
+    if (g0f + 2 < zero_before) cur.z = 0;
     if (n_it > 1) nxt = ldg16(src + 1);
     double lutL[4] = {0, 0, 0, 0}, lutR[4] = {0, 0, 0, 0};
     auto fetch_lut = [&](const uint4 &q, double *l, double *r) {
@@ -246,7 +312,7 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k]);
+        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k], g + k);
         if (g >= job.tile_begin && g + 4 <= f_hi) {
             dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
@@ -258,18 +324,24 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
 #pragma unroll
         for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutR[k] = nR[k]; }
     }
+    if (KW) atomicMax(peak + job.track, pk);
 }
 
 __global__ void __launch_bounds__(128, 2)
-k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
-     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
+k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks, const TrackDev *__restrict__ tdev,
+     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre,
+     double *__restrict__ energy, int *__restrict__ peak) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     const TileJob job = jobs[j];
+    if (job.tile_end <= job.tile_begin) return;           // padding job (tracks get whole warps)
     const ame_track_params *tp = tracks + job.track;
-    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth
-#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre); break; \
-                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre); break;
+    const TrackDev *td = tdev + job.track;
+    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth, bit 5: K-weighting epilogue
+#define AME_EQ_CASE(M) case M: eq_tile<M, false, false>(job, tp, td, luts, in, pre, energy, peak); break; \
+                       case M + 16: eq_tile<M, true, false>(job, tp, td, luts, in, pre, energy, peak); break; \
+                       case M + 32: eq_tile<M, false, true>(job, tp, td, luts, in, pre, energy, peak); break; \
+                       case M + 48: eq_tile<M, true, true>(job, tp, td, luts, in, pre, energy, peak); break;
         AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
         AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
         AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
@@ -353,21 +425,22 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
 // Multiband compressor = pydub compress_dynamic_range per band (:306-308), split by what is sequential:
-//   k_window_flag   (time-parallel)  window rms of the previous look_frames frames; emits the integer rms
-//                                    for frames ABOVE threshold and 0 otherwise (2 B per band frame)
-//   k_att_chain_spec (speculative)   the attenuation recurrence over the flagged frames of one (chunk, band), cut
-//                                    into 64..256 time segments that are walked in parallel from a guessed start
-//                                    and repaired until every segment starts from its predecessor's true end
-//                                    (exact); emits the attenuation after every flagged frame and entering each
-//                                    32-frame group.  Below threshold the reference never releases
-//                                    (max_attenuation = 0 => dec = 0), so unflagged frames are no-ops.
-//   k_att_chain      (sequential)    the same recurrence by one producer + one consumer warp per chain: the
-//                                    fallback for chains whose segments cannot be repaired cheaply, and the
-//                                    whole stage with chain_warps = -1.
-//   k_compress_apply (time-parallel) attenuation in force at a frame = the value stored for the last flagged frame
-//                                    at or before it in its 32-frame group, else the group's entry value;
-//                                    gain = 10^(-att/20), audioop.mul, low.overlay(mid).overlay(high) (:309).
+//   k_window_flag    (time-parallel)  window rms of the previous look_frames frames; emits the integer rms
+//                                     for frames ABOVE threshold and 0 otherwise (2 B per band frame)
+//   k_att_chain      (one CTA per (chunk, band))
+//        phase 0: the CTA streams its rms plane once, coalesced, and COMPACTS the flagged frames in place into a
+//                 dense list of rms values; per 32-frame group it leaves a record {bit mask of flagged frames,
+//                 number of flagged frames before the group}.  Below threshold the reference never releases
+//                 (max_attenuation = 0 => dec = 0), so unflagged frames are no-ops of the recurrence.
+//        phase 1: the attenuation recurrence over the dense list, cut into S segments of EQUAL step count that are
+//                 walked in parallel from a guessed start and repaired until every segment starts from its
+//                 predecessor's true end (exact, see below); emits the attenuation after every flagged frame as a
+//                 dense list (coalescible, no wasted steps, no divergence on silent frames).
+//   k_compress_apply (time-parallel)  attenuation in force at frame i = list[base + popc(mask up to i) - 1] (0 before
+//                                     the first flagged frame of the chunk); gain = 10^(-att/20), audioop.mul,
+//                                     low.overlay(mid).overlay(high) (:309).
 // pydub: rms_at(i) = audioop.rms(frames [max(i-look,0), i)) = (unsigned)sqrt(S / n) with S the exact integer
 // sum of squares and n = 2 * frames.  rms > thresh  <=>  rms >= thr_i  <=>  S >= thr_i^2 * n (integers), so
 // only flagged frames take the square root (S/n is never within 2^-41 of a perfect square unless equal,
@@ -384,7 +457,7 @@ struct MbChunk {           // one chunk of a multiband track (k_compress_apply)
     int64_t mb_begin;      // frame index in the multiband-only packing
     int64_t n;             // frames
     int64_t seg_prefix;    // kSeg-segments in all earlier chunks
-    int64_t ck_begin[3];   // first group slot of each band's chain in the checkpoint array
+    int64_t grp_begin[3];  // first group record of each band's chain
     int32_t track;
     int32_t pad;
 };
@@ -504,398 +577,191 @@ __device__ __forceinline__ double att_update(double att, double m, double inc, d
     return (rising && !above) ? s : r;
 }
 
-constexpr int kChainStages = 2;    // segment buffers in flight between the producer and the consumer warp
+// ------------------------------------------------------------------------------------------------
+// k_att_chain: the attenuation recurrence of one (chunk, band), exact, parallel in time.
+//
+// Phase 0 (all threads): compaction.  The CTA walks its rms plane in tiles of blockDim * 8 frames; every thread
+//   loads 8 rms values (one 16-byte load), a CTA-wide exclusive scan of the flagged counts gives each flagged frame
+//   its rank in the chain, and the rms values are written back IN PLACE at that rank (rank <= frame index, and a
+//   barrier separates a tile's loads from its stores, so nothing is overwritten before it is read).  Four threads
+//   form one 32-frame group and leave its record {mask, rank of its first flagged frame}.
+// Phase 1: speculation and repair over the dense list of n_f steps.  S lanes take S contiguous segments of equal
+//   step count (a multiple of 8).  Pass 1 starts every segment from a guess - the max_attenuation of the step just
+//   before it, which is exactly right whenever the compressor was clamped there; lane 0 from 0, as the reference
+//   resets the attenuation per chunk.  In a repair pass lane t takes the end value lane t-1 produced in the previous
+//   pass; if that differs (bitwise) from the start it used, it walks its segment again carrying BOTH attenuations
+//   (old start, new start - two independent chains in one thread) and stops at the first 8-step block after which
+//   they are bit-equal: from there on what it stored before is right, and so is its old end value.  When no lane's
+//   start changed, every lane has been walked from the true end of its predecessor, i.e. the stored values are
+//   those of the sequential loop.  Trajectories meet whenever both clamp to the same max_attenuation
+//   (att in [tau, M] -> M), which a tracking compressor does constantly.  Where they cannot meet - an attenuation
+//   parked above M for a long stretch releases by M / release_frames per step, hardly at all - each pass settles one
+//   more segment and the lanes of a warp run in lockstep, so the chain degrades to the cost of the sequential loop
+//   (~30 cycles per step), never below it: no fallback kernel is needed.
+// The walk is a software pipeline: rms values two 8-step blocks ahead, table entries (one 32-byte gather per step)
+// one block ahead, 25 cycles per dependent step (profiles/micro/att_chain_latency3.cu).
+// ------------------------------------------------------------------------------------------------
+struct GrpRec { uint32_t mask, base; };   // per 32-frame group of a chain: flagged frames, flagged frames before the group
 
-__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+constexpr int kChainMaxThreads = 256;
 
-// k_att_chain: the strictly sequential part.  Two warps per (chunk, band), four chains per CTA:
-//   a PRODUCER warp walks the 256-frame segments of the rms plane (lane = 8 consecutive frames), compacts the
-//     table entries (M, tau, inc, dec) of the flagged frames into a shared-memory queue in time order, padded to a
-//     multiple of 16 with no-op entries, and later scatters the results (attenuation after every flagged frame ->
-//     att_f, attenuation entering every 32-frame group -> ckpt);
-//   a CONSUMER warp does nothing but the recurrence over those queues: 16 steps per iteration from two
-//     ping-pong register blocks so the shared-memory loads of the next 8 steps are in flight while the current 8
-//     run - 25 cycles per dependent step on B200 (profiles/micro/att_chain_latency3.cu), and segments without
-//     flagged frames cost it one barrier.
-// The two warps are decoupled by kChainStages buffers and named barriers (full[s]: producer arrives / consumer
-// waits; done[s]: consumer arrives / producer waits).
-constexpr int kChainsPerCta = 4;   // consumers = warps 0..3, producers = warps 4..7: one of each per SM sub-partition
-struct ChainSmem {                 // per chain
-    double2 mt[kChainStages][kSeg + 32];     // (M, tau)   (+16 no-op entries, +8 read-ahead slack)
-    double2 id[kChainStages][kSeg + 32];     // (inc, dec)
-    double att[kChainStages][kSeg + 16];     // attenuation after each flagged frame
-    double att_in[kChainStages];             // attenuation entering the segment
-    int total[kChainStages];
-    uint16_t off[kChainStages][32];          // producer bookkeeping for the scatter
-    uint8_t m8[kChainStages][32];
-};
+struct RmsBlk { uint32_t w[4]; };         // 8 consecutive entries of the dense rms list
 
-// One chain on two warps (consumer: producer == false).  `sm` is that pair's queue, bar_base its first named barrier.
-__device__ __forceinline__ void chain_queue_run(const ChainJob &job, ChainSmem &sm, bool producer, int lane, int bar_base,
-                                                const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
-                                                double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames) {
-    auto &s_mt = sm.mt; auto &s_id = sm.id; auto &s_att = sm.att; auto &s_att_in = sm.att_in; auto &s_total = sm.total;
-    auto &s_off = sm.off; auto &s_m8 = sm.m8;
-    const int64_t n = job.n;
-    const int64_t n_seg = (n + kSeg - 1) / kSeg;
-    const int FULL = bar_base, DONE = FULL + kChainStages;   // 2 * kChainStages named barriers of 64 threads
-
-    if (!producer) {
-        // ------------------------------------------------------------------ consumer: the recurrence only
-        double att = 0.0;
-        for (int64_t seg = 0; seg < n_seg; ++seg) {
-            const int st = (int)(seg % kChainStages);
-            named_sync(FULL + st);
-            const int total = s_total[st];
-            if (lane == 0) s_att_in[st] = att;
-            // one active lane is enough (the warp would only repeat the same scalar work 32 times); it also keeps the
-            // shared-memory traffic of the operand loads at 16 B instead of 32 x 16 B per instruction
-            if (total && lane == 0) {
-                const double2 *__restrict__ qmt = s_mt[st];
-                const double2 *__restrict__ qid = s_id[st];
-                double *__restrict__ qa = s_att[st];
-                double2 A0[8], A1[8], B0[8], B1[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { A0[k] = qmt[k]; A1[k] = qid[k]; }
-                for (int j0 = 0; j0 < total; j0 += 16) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { B0[k] = qmt[j0 + 8 + k]; B1[k] = qid[j0 + 8 + k]; }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        att = att_update(att, A0[k].x, A1[k].x, A1[k].y, A0[k].y);
-                        qa[j0 + k] = att;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { A0[k] = qmt[j0 + 16 + k]; A1[k] = qid[j0 + 16 + k]; }   // read-ahead (may be slack)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        att = att_update(att, B0[k].x, B1[k].x, B1[k].y, B0[k].y);
-                        qa[j0 + 8 + k] = att;
-                    }
-                }
-            }
-            att = __shfl_sync(kFull, att, 0);
-            named_arrive(DONE + st);
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- producer: gather, compact, scatter
-    const AttEntry *tbl = tables + (size_t)job.table * 32769;
-    const uint16_t *rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
-    double *af = att_f + (int64_t)job.band * mb_frames + job.mb_begin;
-    double *ck = ckpt + job.ck_begin;
-    const int64_t n_groups = (n + 31) >> 5;
-    const bool vec = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
-
-    auto load_seg = [&](int64_t seg, uint32_t *h) {     // this lane's 8 rms values as 4 words
-        const int64_t i = seg * kSeg + lane * 8;
-        h[0] = h[1] = h[2] = h[3] = 0;
-        if (seg >= n_seg) return;
-        if (vec && i + 8 <= n) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(rp + i));
-            h[0] = q.x; h[1] = q.y; h[2] = q.z; h[3] = q.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (i + k < n) h[k >> 1] |= (uint32_t)__ldg(rp + i + k) << ((k & 1) * 16);
-        }
-    };
-    // scatter the results of a finished segment: attenuation after each flagged frame, and entering each group
-    auto flush = [&](int64_t seg) {
-        const int st = (int)(seg % kChainStages);
-        named_sync(DONE + st);
-        const int total = s_total[st];
-        double ge = s_att_in[st];
-        if (total) {
-            const double *qa = s_att[st];
-            const unsigned m8 = s_m8[st][lane];
-            int slot = s_off[st][lane];
-            // flagged frames before group g = exclusive count at lane 4g; lane g (< 8) keeps it
-            const int before_grp = s_off[st][(lane & 7) * 4];
-            if (before_grp) ge = qa[before_grp - 1];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (m8 & (1u << k)) af[seg * kSeg + lane * 8 + k] = qa[slot++];
-        }
-        if (lane < 8 && seg * 8 + lane < n_groups) ck[seg * 8 + lane] = ge;
-    };
-
-    uint32_t cur[4], nx1[4], nx2[4];                   // rms words are fetched two segments ahead
-    load_seg(0, cur);
-    load_seg(1, nx1);
-    for (int64_t seg = 0; seg < n_seg; ++seg) {
-        const int st = (int)(seg % kChainStages);
-        load_seg(seg + 2, nx2);
-        if (seg >= kChainStages) flush(seg - kChainStages);    // also frees stage st
-        unsigned m8 = 0;
+// entries [i, i+8) of the list, entries at or past `lim` read as 0 (= the no-op table entry).  Plain loads: the list
+// was written by this kernel.
+__device__ __forceinline__ RmsBlk list_load(const uint16_t *lp, int64_t i, int64_t lim, bool vec) {
+    RmsBlk q;
+    q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0;
+    if (vec && i + 8 <= lim) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(lp + i);
+        q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
+    } else if (i < lim) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if ((cur[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
-        const int cnt = __popc(m8);
-        int incl = cnt;                                // inclusive scan of the per-lane counts
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(kFull, incl, 31);
-        if (total) {
-            double2 *qmt = s_mt[st], *qid = s_id[st];
-            int slot = incl - cnt;
-            s_m8[st][lane] = (uint8_t)m8;
-            s_off[st][lane] = (uint16_t)slot;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned r = (cur[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                if (r) {
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(tbl + r));       // (M, inc)
-                    const double2 b = __ldg(reinterpret_cast<const double2 *>(tbl + r) + 1);   // (dec, tau)
-                    qmt[slot] = make_double2(a.x, b.y);
-                    qid[slot] = make_double2(a.y, b.x);
-                    ++slot;
-                }
-            }
-            // no-op entries: M < 0 => "above", dec = 0 => att unchanged
-            if (lane < 16) { qmt[total + lane] = make_double2(-1.0, 0.0); qid[total + lane] = make_double2(0.0, 0.0); }
-        }
-        if (lane == 0) s_total[st] = total;
-        named_arrive(FULL + st);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { cur[k] = nx1[k]; nx1[k] = nx2[k]; }
-    }
-    for (int64_t seg = (n_seg > kChainStages ? n_seg - kChainStages : 0); seg < n_seg; ++seg) flush(seg);
-}
-
-__global__ void __launch_bounds__(kChainsPerCta * 64)
-k_att_chain(const ChainJob *__restrict__ jobs, int n_jobs, const uint16_t *__restrict__ rms,
-            const AttEntry *__restrict__ tables, double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames,
-            const int *__restrict__ only) {      // only != NULL: just the chains k_att_chain_spec left to this kernel
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    // Warp w of a CTA lands on SM sub-partition w % 4.  With 64-thread CTAs every consumer warp sat on sub-partitions
-    // 1 and 3 and, at ~8 chains per SM, four latency-bound recurrences shared one issue port (24 instead of 10
-    // cycles/frame for 1152 chains).  Four chains per CTA put one consumer and one producer on every sub-partition.
-    const int warp = threadIdx.x >> 5;
-    const int chain = warp & (kChainsPerCta - 1);
-    const int job_i = blockIdx.x * kChainsPerCta + chain;
-    if (job_i >= n_jobs || (only && !only[job_i])) return;   // both warps of that chain leave; barriers are per chain
-    chain_queue_run(jobs[job_i], reinterpret_cast<ChainSmem *>(s_raw)[chain], warp >= kChainsPerCta, threadIdx.x & 31,
-                    chain * 2 * kChainStages, rms, tables, ckpt, att_f, mb_frames);
-}
-
-// k_att_chain_spec: the recurrence, made parallel in time by SPECULATION AND REPAIR - exact, not approximate.
-// One CTA per (chunk, band); S = n_lanes of its threads cut the chunk into S contiguous segments and every lane
-// walks its own segment (the lanes of a warp run in lockstep, so a step of the 25-cycle dependent chain advances
-// 32 segments at once):
-//   pass 1   every lane starts from attenuation 0 (lane 0 really does - the reference resets it per chunk);
-//   repair   lane t takes the end value lane t-1 produced in the previous pass.  If that differs from the start it
-//            used, it walks its segment again carrying BOTH attenuations (old start, new start - two independent
-//            chains in one thread, no extra latency) and stops at the first frame where they are bit-equal: from
-//            there on the trajectory it stored before is the right one, and so is its old end value.  A lane that
-//            never meets publishes a new end value;
-//   until no lane's start changed.  By induction every lane has then been walked from the true end of its
-//   predecessor, i.e. the stored values are those of the sequential loop.  A chain that does not settle within its
-//   repair budget is redone by two warps of the CTA as the producer / consumer pair of k_att_chain (or, from a
-//   one-warp CTA, flagged in gave_up[] for the filtered k_att_chain launch that follows).
-// Trajectories meet whenever both clamp to the same max_attenuation (att in [tau, M] -> M), which the compressor
-// does all the time while it tracks the level: on the bench tracks 0.3k-20k frames after a segment start (two or
-// three passes).  A signal that never clamps would degrade to one segment per pass; the budget below cuts that off.
-// Unflagged frames carry rms 0 and table entry 0 (M = inc = dec = tau = 0) is a no-op, so the walk needs no branch
-// per frame; 8-frame blocks without any flagged frame are skipped.
-// Emits the attenuation after every flagged frame (att_f, sparse) and entering every 32-frame group (ckpt).
-constexpr int kChainMaxThreads = 256;
-constexpr int kWalkBlock = 16;     // frames per walker iteration = one 32-byte rms load
-
-struct ChainCtx {
-    const uint16_t *rp;        // rms plane of this chain
-    const AttEntry *tbl;
-    double *af, *ck;
-    int64_t n;
-    bool vec;                  // rp is 32-byte aligned
-};
-
-struct RmsBlock { uint32_t w[kWalkBlock / 2]; };
-
-__device__ __forceinline__ RmsBlock chain_load_rms(const ChainCtx &c, int64_t i) {   // rms of frames i..i+15, 0 past the end
-    RmsBlock q;
-#pragma unroll
-    for (int k = 0; k < kWalkBlock / 2; ++k) q.w[k] = 0;
-    if (i + kWalkBlock <= c.n && c.vec) {
-        // volatile: must stay under the alignment test (a plain asm counts as pure and may be executed speculatively)
-        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(q.w[0]), "=r"(q.w[1]), "=r"(q.w[2]), "=r"(q.w[3]), "=r"(q.w[4]), "=r"(q.w[5]), "=r"(q.w[6]), "=r"(q.w[7])
-                     : "l"(c.rp + i));
-    } else if (i < c.n) {
-#pragma unroll
-        for (int k = 0; k < kWalkBlock; ++k)
-            if (i + k < c.n) q.w[k >> 1] |= (uint32_t)__ldg(c.rp + i + k) << ((k & 1) * 16);
+            if (i + k < lim) q.w[k >> 1] |= (uint32_t)lp[i + k] << ((k & 1) * 16);
     }
     return q;
 }
 
-__device__ __forceinline__ bool chain_any(const RmsBlock &q, int h) {     // a flagged frame in half h of the block?
-    return (q.w[4 * h] | q.w[4 * h + 1] | q.w[4 * h + 2] | q.w[4 * h + 3]) != 0;
-}
-
-// table entries of the 8 frames of half h of a block: one 32-byte load per flagged frame, the no-op entry otherwise.
-// (plain asm, not volatile: the table is constant and tbl + r is always a valid aligned entry, so the compiler may
-// schedule - or speculate - the loads as it likes)
-__device__ __forceinline__ void chain_entries(AttEntry *e, const AttEntry *tbl, const RmsBlock &q, int h) {
+// table entries of the 8 steps of a block: one 32-byte gather each (entry 0 is all zeros = no-op).  Plain asm, not
+// volatile: the table is constant and tbl + r is always a valid aligned entry, so the compiler may schedule the loads
+// as it likes.
+__device__ __forceinline__ void list_entries(AttEntry *e, const AttEntry *tbl, const RmsBlk &q) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const unsigned r = (q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu;
-        e[k] = AttEntry{0.0, 0.0, 0.0, 0.0};
-        if (r) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e[k].m), "=d"(e[k].inc), "=d"(e[k].dec), "=d"(e[k].tau) : "l"(tbl + r));
+        const unsigned r = (q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e[k].m), "=d"(e[k].inc), "=d"(e[k].dec), "=d"(e[k].tau) : "l"(tbl + r));
     }
 }
 
-struct SegStat { double max_m, sum_dec; int n_flag, n_grp; };   // of a segment: largest max_attenuation, total release if always above
-                                                                // it, flagged frames, 8-frame groups holding one
-
-// 8 steps of the recurrence over frames i..i+7 (half h of block q); true when DUAL and a == b afterwards.
-// The first (single) walk also gathers the segment statistics.
+// 8 steps of the recurrence (steps [i, i+8) of the list) from attenuation b - with DUAL also from a - storing the
+// b trajectory.  True when DUAL and a == b afterwards.
 template <bool DUAL>
-__device__ __forceinline__ bool chain_step8(const ChainCtx &c, const RmsBlock &q, int h, const AttEntry *e, int64_t i, double &a, double &b,
-                                            SegStat &st) {
-    if (!chain_any(q, h)) return false;
-    if (!DUAL) ++st.n_grp;
+__device__ __forceinline__ bool list_step8(const AttEntry *e, double *al, int64_t i, int64_t lim, bool avec, double &a, double &b) {
+    double o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         b = att_update(b, e[k].m, e[k].inc, e[k].dec, e[k].tau);
         if (DUAL) a = att_update(a, e[k].m, e[k].inc, e[k].dec, e[k].tau);
-        const bool flagged = ((q.w[4 * h + (k >> 1)] >> ((k & 1) * 16)) & 0xffffu) != 0;
-        if (!DUAL) { st.max_m = fmax(st.max_m, e[k].m); st.sum_dec += e[k].dec; st.n_flag += flagged; }
-        if (flagged) c.af[i + k] = b;
+        o[k] = b;
+    }
+    if (avec && i + 8 <= lim) {
+        double2 *d = reinterpret_cast<double2 *>(al + i);
+        d[0] = make_double2(o[0], o[1]); d[1] = make_double2(o[2], o[3]);
+        d[2] = make_double2(o[4], o[5]); d[3] = make_double2(o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i + k < lim) al[i + k] = o[k];
     }
     return DUAL && __double_as_longlong(a) == __double_as_longlong(b);
 }
 
-// Walk frames [b0, b1) (b0 a multiple of 32) from attenuation b; with DUAL also from a, returning true at the first
-// 8-frame group after which the two are bit-equal.  b holds the attenuation reached.  The rms words run two blocks
-// ahead of the recurrence and the table entries one half block ahead (two register blocks, as many loads in flight
-// as the 8 dependent steps they hide behind).
+// steps [b0, b1) of the list (b0 a multiple of 8) from attenuation b; with DUAL also from a, returning true after the
+// first block that leaves the two bit-equal.  b holds the attenuation reached.
 template <bool DUAL>
-__device__ __forceinline__ bool chain_walk(const ChainCtx &c, int64_t b0, int64_t b1, double a, double &b, SegStat &st) {
+__device__ __forceinline__ bool list_walk(const uint16_t *lp, const AttEntry *tbl, double *al, int64_t b0, int64_t b1, bool vec,
+                                          bool avec, double a, double &b) {
     if (b0 >= b1) return false;
-    RmsBlock cur = chain_load_rms(c, b0), nxt = chain_load_rms(c, b0 + kWalkBlock);
+    RmsBlk r0 = list_load(lp, b0, b1, vec), r1 = list_load(lp, b0 + 8, b1, vec);
     AttEntry ea[8], eb[8];
-    chain_entries(ea, c.tbl, cur, 0);
-    for (int64_t i = b0; i < b1; i += kWalkBlock) {
-        const RmsBlock nn = chain_load_rms(c, i + 2 * kWalkBlock);
-        if ((i & 31) == 0) c.ck[i >> 5] = b;
-        if (!chain_any(cur, 0) && !chain_any(cur, 1)) {      // 16 silent frames: a dozen instructions instead of ~150
-            if (chain_any(nxt, 0)) chain_entries(ea, c.tbl, nxt, 0);
-            cur = nxt; nxt = nn;
-            continue;
-        }
-        chain_entries(eb, c.tbl, cur, 1);
-        if (chain_step8<DUAL>(c, cur, 0, ea, i, a, b, st)) return true;
-        chain_entries(ea, c.tbl, nxt, 0);
-        if (chain_step8<DUAL>(c, cur, 1, eb, i + 8, a, b, st)) return true;
-        cur = nxt; nxt = nn;
+    list_entries(ea, tbl, r0);
+    for (int64_t i = b0; i < b1; i += 16) {
+        r0 = list_load(lp, i + 16, b1, vec);
+        list_entries(eb, tbl, r1);
+        if (list_step8<DUAL>(ea, al, i, b1, avec, a, b)) return true;
+        if (i + 8 >= b1) break;
+        r1 = list_load(lp, i + 24, b1, vec);
+        list_entries(ea, tbl, r0);
+        if (list_step8<DUAL>(eb, al, i + 8, b1, avec, a, b)) return true;
     }
     return false;
 }
 
 __global__ void __launch_bounds__(kChainMaxThreads)
-k_att_chain_spec(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ rms, const AttEntry *__restrict__ tables,
-                 double *__restrict__ ckpt, double *__restrict__ att_f, int64_t mb_frames, int *__restrict__ gave_up,
-                 int n_lanes) {            // segments per chain (<= blockDim.x; threads past it only serve the fallback)
-    __shared__ double s_end[kChainMaxThreads], s_max_m[kChainMaxThreads], s_dec[kChainMaxThreads];
-    __shared__ int s_nflag[kChainMaxThreads], s_ngrp[kChainMaxThreads], s_stuck, s_budget;
-    __shared__ short s_prev[kChainMaxThreads];
+k_att_chain(const ChainJob *__restrict__ jobs, uint16_t *rms, const AttEntry *__restrict__ tables, GrpRec *__restrict__ grp,
+            double *att, int64_t mb_frames, int n_lanes, int *__restrict__ stats) {   // stats[chain] = {flagged steps, passes}
+    __shared__ int s_warp[2][kChainMaxThreads / 32];
+    __shared__ double s_end[kChainMaxThreads];
     const ChainJob job = jobs[blockIdx.x];
-    const int S = n_lanes, t = threadIdx.x;     // threads t >= S get an empty segment [n, n)
-    ChainCtx c;
-    c.rp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
-    c.tbl = tables + (size_t)job.table * 32769;
-    c.af = att_f + (int64_t)job.band * mb_frames + job.mb_begin;
-    c.ck = ckpt + job.ck_begin;
-    c.n = job.n;
-    c.vec = (reinterpret_cast<uintptr_t>(c.rp) & 31) == 0;
-    // whole 32-frame groups per segment: a checkpoint and a 32-byte rms load never straddle two lanes
-    const int64_t seg = (((c.n + S - 1) / S) + 31) & ~(int64_t)31;
-    const int64_t b0 = min(c.n, (int64_t)t * seg), b1 = min(c.n, b0 + seg);
-    // First guess for the attenuation entering the segment: the max_attenuation of the last flagged frame before it
-    // (looked for in the 64 frames in front), which is exactly right whenever the compressor was clamped to it there -
-    // about every second frame while it tracks a rising level - and costs nothing when it is wrong; else 0.
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, n_warps = (blockDim.x + 31) >> 5;
+    uint16_t *lp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
+    double *al = att + (int64_t)job.band * mb_frames + job.mb_begin;
+    GrpRec *gr = grp + job.grp_begin;
+    const AttEntry *tbl = tables + (size_t)job.table * 32769;
+    const int64_t n = job.n;
+    const bool vec = (reinterpret_cast<uintptr_t>(lp) & 15) == 0;
+    const bool avec = (reinterpret_cast<uintptr_t>(al) & 15) == 0;
+
+    // ---- phase 0: compact the flagged frames of the rms plane in place, leave the group records -----------------
+    int64_t running = 0;
+    const int64_t tile = (int64_t)blockDim.x * 8;
+    int par = 0;
+    RmsBlk qn = list_load(lp, (int64_t)t * 8, n, vec);
+    for (int64_t t0 = 0; t0 < n; t0 += tile, par ^= 1) {
+        const int64_t i = t0 + (int64_t)t * 8;
+        const RmsBlk q = qn;
+        qn = list_load(lp, i + tile, n, vec);     // next tile's words in flight (they lie above every store of this tile)
+        unsigned m8 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
+        const int cnt = __popc(m8);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[par][wid] = incl;
+        // the four threads of a 32-frame group sit in one warp (t & 3 == 0 leads)
+        const unsigned m1 = __shfl_down_sync(kFull, m8, 1), m2 = __shfl_down_sync(kFull, m8, 2), m3 = __shfl_down_sync(kFull, m8, 3);
+        __syncthreads();          // every load of this tile has been consumed; s_warp[par] is complete
+        int before = 0, total = 0;
+        for (int w = 0; w < n_warps; ++w) {
+            const int c = s_warp[par][w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        const int64_t rank = running + before + incl - cnt;
+        if ((t & 3) == 0 && i < n) gr[i >> 5] = GrpRec{m8 | (m1 << 8) | (m2 << 16) | (m3 << 24), (uint32_t)rank};
+        int64_t slot = rank;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m8 & (1u << k)) lp[slot++] = (uint16_t)((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+        running += total;
+        // no second barrier: the next tile uses the other half of s_warp, reads frames >= t0 + tile, and every store of
+        // this tile lands below t0 + tile
+    }
+    const int64_t n_f = running;
+    __syncthreads();              // the dense list is complete and visible to the CTA
+
+    // ---- phase 1: the recurrence over n_f steps in S segments, speculation and repair ---------------------------
+    int S = n_lanes < 1 ? 1 : (n_lanes > (int)blockDim.x ? (int)blockDim.x : n_lanes);
+    int64_t seg = (((n_f + S - 1) / S) + 7) & ~(int64_t)7;
+    if (seg < 64) seg = 64;                                   // a lane is not worth less than a few blocks
+    const int S_used = (int)((n_f + seg - 1) / seg);
+    const int64_t b0 = min(n_f, (int64_t)t * seg), b1 = min(n_f, b0 + seg);
     double start = 0.0;
-    if (t > 0 && t < S && b0 < b1) {
-        const int64_t lo = max((int64_t)0, b0 - 64);
-        for (int64_t i = b0 - 1; i >= lo; --i) {
-            const unsigned r = __ldg(c.rp + i);
-            if (r) { start = c.tbl[r].m; break; }
-        }
-    }
+    if (t > 0 && b0 < b1) start = tbl[lp[b0 - 1]].m;
     double end = start;
-    SegStat st{0.0, 0.0, 0, 0};
-    chain_walk<false>(c, b0, b1, 0.0, end, st);
-    // What the first walk tells, before any repair is paid for (thread 0, S <= 256 segments):
-    // * budget.  Measured on B200 (profiles/r01e_summary.md): a repair pass costs a lone warp ~120 cycles per frame of
-    //   every 8-frame group that holds a flagged frame (the walk skips the others; the slowest lane carries ~1.3x the
-    //   mean) plus ~5 per frame of the segment for scanning; the queue kernel, which compacts the flagged frames,
-    //   25 cycles per flagged frame plus ~4 per frame.  Speculation may cost 80 % of what the queue kernel needs for the chain: a
-    //   band at 12 % flagged frames spread over every group is cheap for the queue and dear to repair, one at 40 %
-    //   in bursts the other way round.
-    // * forecast.  Follow a lower bound of the TRUE attenuation through the segments: where it enters a segment above
-    //   everything that segment can ask for, even after all the release it could get there, the true trajectory never
-    //   clamps in it, cannot meet the speculation, and hands the problem to the next lane.  A run of such segments
-    //   costs one repair pass each (one loud passage, then a bed just over threshold: the reference releases by
-    //   M / release_frames per frame, i.e. hardly at all); a run far longer than the budget is a chain for k_att_chain.
-    // Both only decide WHO computes the chain; what is stored is decided by the bit-equality test alone.
-    s_end[t] = end; s_max_m[t] = st.max_m; s_dec[t] = st.sum_dec; s_nflag[t] = st.n_flag; s_ngrp[t] = st.n_grp;
-    __syncthreads();
-    if (t == 0) {
-        double lb = s_end[0];
-        int run = 0, longest = 0;
-        long long flagged = s_nflag[0], groups = s_ngrp[0];
-        for (int u = 1; u < S; ++u) {
-            flagged += s_nflag[u];
-            groups += s_ngrp[u];
-            const double lo = lb - 1.000001 * s_dec[u];
-            if (lb > 0.0 && lo > s_max_m[u]) { lb = lo; run += s_nflag[u] != 0; longest = max(longest, run); }   // silent segments re-walk for free
-            else { lb = s_end[u]; run = 0; }
-        }
-        const long long budget = 4 * (25 * flagged + 4 * c.n) / (5 * (1250 * groups / S + 5 * seg)) - 1;
-        s_budget = (int)max(2LL, min(budget, (long long)S));
-        s_stuck = longest + 2 > s_budget;      // a run of L such segments needs about L + 2 repairs
-    }
-    __syncthreads();
-    // a segment without a flagged frame hands its start on unchanged: lane t takes the end of the last lane before it
-    // that has one (else a sparse band would pay a pass per silent segment just to pass a number along).  Silent
-    // lanes still re-walk when their start changes - a skip per 16 frames - to refresh their checkpoints.
-    {
-        int u = t - 1;
-        while (u >= 0 && s_nflag[u] == 0) --u;
-        s_prev[t] = (short)u;
-    }
-    const int max_repairs = s_budget;
-    int repairs = 0, stuck = s_stuck;
-    while (!stuck) {
+    list_walk<false>(lp, tbl, al, b0, b1, vec, avec, 0.0, end);
+    int passes = 1;
+    for (;;) {
         s_end[t] = end;
         __syncthreads();
-        const double from = s_prev[t] >= 0 ? s_end[s_prev[t]] : 0.0;
-        const bool redo = t < S && __double_as_longlong(from) != __double_as_longlong(start);
-        const int n_redo = __syncthreads_count(redo);      // also orders the reads of s_end before the next round's writes
+        const double from = (t > 0 && t < S_used) ? s_end[t - 1] : 0.0;
+        const bool redo = t < S_used && __double_as_longlong(from) != __double_as_longlong(start);
+        const int n_redo = __syncthreads_count(redo);     // also orders the reads of s_end before the next round's writes
         if (!n_redo) break;
-        if (repairs >= max_repairs || (repairs >= 2 && 2 * n_redo > S)) { stuck = 1; break; }   // over budget / not settling
-        ++repairs;
+        ++passes;
         if (redo) {
             double b = from;
-            if (!chain_walk<true>(c, b0, b1, start, b, st)) end = b;
+            if (!list_walk<true>(lp, tbl, al, b0, b1, vec, avec, start, b)) end = b;
             start = from;
         }
     }
-    // A chain that will not settle is strictly sequential: with two warps or more the CTA turns into one producer /
-    // consumer pair of the queue kernel on the spot (the other chains of the launch keep repairing meanwhile);
-    // a single-warp CTA leaves it to the filtered k_att_chain launch that follows.
-    const bool here = stuck && blockDim.x >= 64;
-    if (t == 0) gave_up[blockIdx.x] = stuck && !here;
-    if (here && t < 64) {
-        extern __shared__ __align__(16) unsigned char s_raw[];
-        chain_queue_run(job, *reinterpret_cast<ChainSmem *>(s_raw), t >= 32, t & 31, 1, rms, tables, ckpt, att_f, mb_frames);
-    }
+    if (stats && t == 0) { stats[2 * blockIdx.x] = (int)min(n_f, (int64_t)0x7fffffff); stats[2 * blockIdx.x + 1] = passes; }
 }
 
 __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
@@ -905,19 +771,20 @@ __device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fboun
     return __double2int_rd(v);
 }
 
-// k_compress_apply: one warp per 256-frame segment, all three bands.  The attenuation in force at a frame is
-// the value k_att_chain stored for the last flagged frame at or before it inside its 32-frame group, or the
-// group's entry value; gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)), skipped
-// when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
-// pydub db_to_float(-att) = 10 ** (-att / 20); out of line so the 24 call sites of k_compress_apply share one copy
-// (the fully inlined kernel thrashed the instruction cache: stall_no_instruction 1.7 per issue)
+// pydub db_to_float(-att) = 10 ** (-att / 20); out of line so the call sites of k_compress_apply share one copy
+// (the fully inlined kernel thrashed the instruction cache: stall_no_instruction 1.7 per issue).  CUDA exp10 is within
+// 1 ulp of the correctly rounded value, CPython's is glibc pow: a different last bit of the gain moves x * gain by
+// < 4e-12 LSB, so floor() flips only when the product is that close to an integer (parity decisions).
 __device__ __noinline__ double gain_of_att(double att) { return exp10(-att / 20.0); }
 
+// k_compress_apply: one warp per 256-frame segment, all three bands.  The attenuation in force at a frame is the
+// list value of the last flagged frame at or before it: rank = group base + popc(mask up to the lane); 0 before the
+// first flagged frame of the chunk.  gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)),
+// skipped when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
 __global__ void __launch_bounds__(128)
 k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
-                 const int16_t *__restrict__ bands, const uint16_t *__restrict__ rms,
-                 const double *__restrict__ ckpt, const double *__restrict__ att_f, int16_t *__restrict__ pre,
-                 int64_t mb_frames) {
+                 const int16_t *__restrict__ bands, const GrpRec *__restrict__ grp, const double *__restrict__ att,
+                 int16_t *__restrict__ pre, int64_t mb_frames) {
     const int64_t seg = seg_lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (seg >= seg_hi) return;
     const int lane = threadIdx.x & 31;
@@ -930,38 +797,37 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_l
     const int64_t lseg = seg - ck.seg_prefix;
     const int64_t f0 = lseg * kSeg;
     const int64_t n = ck.n;
-    // issue every load of the segment first (24 groups x {rms, band word, entry attenuation}): the kernel is
-    // bound by memory latency, not by arithmetic
-    unsigned rv[3][8];
+    // issue every load of the segment first (24 groups x {record, band word}), then the attenuations
     uint32_t wv[3][8];
-    double ce[3][8];
+    GrpRec rec[3][8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)b * mb_frames + ck.mb_begin;
-        const uint16_t *rp = rms + (int64_t)b * mb_frames + ck.mb_begin;
-        const double *cp = ckpt + ck.ck_begin[b] + lseg * 8;
+        const GrpRec *gp = grp + ck.grp_begin[b] + lseg * 8;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const int64_t i = f0 + g * 32 + lane;
-            const bool valid = i < n;
-            rv[b][g] = valid ? (unsigned)__ldg(rp + i) : 0u;
-            wv[b][g] = valid ? __ldg(bp + i) : 0u;
-            ce[b][g] = (f0 + g * 32 < n) ? __ldg(cp + g) : 0.0;
+            wv[b][g] = (i < n) ? __ldg(bp + i) : 0u;
+            const uint2 r = (f0 + g * 32 < n) ? __ldg(reinterpret_cast<const uint2 *>(gp + g)) : make_uint2(0u, 0u);
+            rec[b][g] = GrpRec{r.x, r.y};
         }
     }
     int accl[8], accr[8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-        const double *ap = att_f + (int64_t)b * mb_frames + ck.mb_begin;
+        const double *ap = att + (int64_t)b * mb_frames + ck.mb_begin;
+        double av[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const unsigned rank = rec[b][g].base + __popc(rec[b][g].mask & (0xffffffffu >> (31 - lane)));
+            av[g] = rank ? __ldg(ap + (rank - 1)) : 0.0;
+        }
         double c_att = 0.0, c_fac = 1.0;           // per-lane cache of the last gain computed
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-            const int64_t i = f0 + g * 32 + lane;
             const uint32_t w = wv[b][g];
             int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
-            const unsigned flags = __ballot_sync(kFull, rv[b][g] != 0);
-            const unsigned below = flags & (0xffffffffu >> (31 - lane));
-            const double mine = below ? __ldg(ap + (i - lane) + (31 - __clz(below))) : ce[b][g];
+            const double mine = av[g];
             if (mine != 0.0) {
                 if (mine != c_att) { c_att = mine; c_fac = gain_of_att(mine); }
                 l = mul_floor(l, c_fac);

@@ -39,7 +39,8 @@ class MasterPlan:
     """
 
     def __init__(self, lengths, sample_rates, settings_list, device=0, chunk_seconds=30, host_io=False,
-                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None, n_waves=1, chain_warps=0):
+                 eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None, n_waves=1, chain_warps=0,
+                 n_slots=0, fuse_kw=True, precision="exact"):
         self.lib = L.load()
         n = len(lengths)
         if n == 0:
@@ -64,7 +65,8 @@ class MasterPlan:
                                          chunk_seconds, lut_index, self.halos[i])
         self.params = arr
         opt = L.PlanOptions(int(eq_tile_frames), int(xover_tile_frames), int(kw_tile_subblocks), 1 if host_io else 0,
-                            int(n_waves), int(chain_warps))
+                            int(n_waves), int(chain_warps), int(n_slots), 0 if fuse_kw else -1,
+                            {"exact": 0, "fp32": 1}[precision])
         h = C.c_void_p()
         L.check(self.lib.ame_plan_create(int(device), arr, n, C.byref(opt), C.byref(h)))
         self.handle = h
@@ -129,6 +131,21 @@ class MasterPlan:
     @property
     def workspace_bytes(self):
         return int(self.lib.ame_plan_workspace_bytes(self.handle))
+
+    @property
+    def n_waves(self):
+        return int(self.lib.ame_plan_wave_count(self.handle))
+
+    @property
+    def n_slots(self):
+        return int(self.lib.ame_plan_slot_count(self.handle))
+
+    def chain_stats(self):
+        """Compressor recurrence of the last call: chains, flagged steps (total, longest chain), passes (total, max)."""
+        v = [C.c_int64() for _ in range(4)]
+        mp = C.c_int32()
+        L.check(self.lib.ame_plan_chain_stats(self.handle, *[C.byref(x) for x in v], C.byref(mp)))
+        return dict(chains=v[0].value, steps=v[1].value, max_steps=v[2].value, passes=v[3].value, max_passes=mp.value)
 
     # -- the path -------------------------------------------------------------------------------
     @staticmethod

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AME_ABI_VERSION 4
+#define AME_ABI_VERSION 5
 #define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
@@ -128,9 +128,18 @@ typedef struct {
                                     of one wave overlaps the bulk kernels of the others, and ame_master_host also
                                     overlaps the H2D copy of wave w+1 and the D2H copy of wave w-1 with the kernels of
                                     wave w.  Tiles shrink with the wave, so more waves = more filter warm-up work */
-    int32_t chain_warps;         /* compressor recurrence: 0 = k_att_chain_spec with 2..4 warps (x32 speculative time
-                                    segments) per chain, chosen per launch; 1..8 = that many warps; -1 = k_att_chain
-                                    alone (one lane per chain, the sequential form) */
+    int32_t chain_warps;         /* compressor recurrence (k_att_chain): 0 = 4..8 warps (x32 speculative time segments)
+                                    per chain, chosen per launch; 1..8 = that many warps; -1 = ONE lane per chain, i.e.
+                                    the sequential loop of the reference (the baseline the speculation is tested against) */
+    int32_t n_slots;             /* workspace slots: wave w runs in slot w % n_slots on that slot's stream, so only
+                                    n_slots waves are in flight and the plan's workspace is that of n_slots waves, not
+                                    of the batch (1024 tracks fit one GPU).  <= 0: min(n_waves, 4) */
+    int32_t fuse_kw;             /* 0 = tracks without a multiband stage get their K-weighting / 100 ms energies in
+                                    the k_eq epilogue (the pre-normalisation signal is not read again); -1 = always
+                                    the separate k_kweight_energy pass (A/B, tests) */
+    int32_t precision;           /* 0 = FP64 filters (results equal to the reference's float64 scipy path);
+                                    1 = EQ cascade in FP32 (A/B measurement only: +-1 LSB truncation flips, which the
+                                    make-up gain of the loudness stage multiplies - DESIGN.md) */
 } ame_plan_options;
 
 typedef struct ame_plan ame_plan;
@@ -157,6 +166,11 @@ int64_t ame_plan_total_frames(const ame_plan *plan);     /* padded length of the
 size_t ame_plan_workspace_bytes(const ame_plan *plan);
 int64_t ame_plan_launch_count(const ame_plan *plan);      /* kernels launched by the last call */
 int32_t ame_plan_wave_count(const ame_plan *plan);
+int32_t ame_plan_slot_count(const ame_plan *plan);
+/* statistics of the compressor recurrence of the last call (benchmarks): chains, flagged steps in total and in the
+ * longest chain, passes (1 + repairs) in total and at most */
+int ame_plan_chain_stats(ame_plan *plan, int64_t *n_chains, int64_t *steps, int64_t *max_steps, int64_t *passes,
+                         int32_t *max_passes);
 
 /* per-kernel device timing with CUDA events on the processing stream(s) (benchmarks): enable, run up to 64
  * ame_master_* / ame_measure_* calls, then read the summed milliseconds and launch counts per kernel (with
@@ -182,12 +196,13 @@ int ame_master_host(ame_plan *plan, const int16_t *h_in, int16_t *h_out, ame_tra
 
 /* two-phase form for tracks that are time-sharded across GPUs: phase 1 stops after the gating
  * histograms (d_hist: DEVICE int64[n_tracks][1000], caller-owned so it can be all-reduced with
- * NCCL); phase 2 derives the gain from (possibly all-reduced) histograms and applies it. */
+ * NCCL); phase 2 derives the gain from (possibly all-reduced) histograms and applies it.
+ * Every wave must keep its pre-normalisation signal between the two calls: n_slots == n_waves. */
 int ame_measure_device(ame_plan *plan, const int16_t *d_in, int64_t *d_hist, void *stream);
 int ame_normalize_device(ame_plan *plan, const int64_t *d_hist, int16_t *d_out,
                          ame_track_result *results, void *stream);
 
-/* stage entry points (parity taps; each replaces the named reference function) ------------------ */
+/* stage entry points (parity taps; each replaces the named reference function; plans with ONE wave) */
 /* warmth -> int16 -> EQ -> width -> int16: apply_analog_character, audio_segment_to_float_array,
  * apply_eq_to_samples, apply_stereo_width, float_array_to_audio_segment (:192-196) */
 int ame_stage_eq(ame_plan *plan, const int16_t *d_in, int16_t *d_pre, void *stream);

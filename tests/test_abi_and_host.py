@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ame.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.ame_abi_version() == 4
+    assert lib.ame_abi_version() == _lib.AME_ABI_VERSION == 5
 
 
 def test_struct_layout_matches(lib):
