@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -129,6 +130,11 @@ struct Wave {
     int64_t seg_lo = 0, seg_hi = 0;
     int slot = 0;                                  // workspace slot (and stream) this wave runs in
     int64_t mb_frames = 0, n_groups = 0;           // of the wave's own multiband packing
+    bool xover_uni = false, kw_uni = false;        // all multiband tracks share the crossover / all k_kweight_energy tracks the K filter
+    XoverCfg xover{};
+    KwCfg kw{};
+    struct EqLaunch { int job_lo, job_n, table; bool plain, fused; };   // which of k_eq / k_eq_kw have work in it
+    std::vector<EqLaunch> eq_launches;             // k_eq launches of the wave: one per table of <= kMaxEqCfg configurations
 };
 
 // Per-wave workspace.  A plan has n_slots of them; wave w runs in slot w % n_slots on that slot's stream, so a slot is
@@ -136,7 +142,10 @@ struct Wave {
 struct Slot {
     int16_t *pre = nullptr;      // pre-normalisation int16 of the wave (the signal the reference materialises at the concat)
     int16_t *bands = nullptr;    // 3 planes of mb_frames frames
-    uint16_t *rms = nullptr;     // 3 planes: integer window rms of flagged frames, compacted in place by k_att_chain
+    uint16_t *rms = nullptr;     // 3 planes: integer window rms of flagged frames, 0 elsewhere
+    uint16_t *list = nullptr;    // 3 planes: per chain the rms values of its flagged frames, dense
+    int *tile_cnt = nullptr;     // flagged frames per k_window_flag tile
+    int *n_flagged = nullptr;    // flagged frames per chain
     GrpRec *grp = nullptr;       // per 32-frame group of every chain
     double *att = nullptr;       // 3 planes: attenuation after every flagged frame, dense per chain
     cudaStream_t stream = nullptr;
@@ -155,8 +164,10 @@ struct ame_plan {
     int64_t total_frames = 0;             // padded
     int64_t mb_frames = 0;                // padded; the largest wave's multiband packing = plane stride of every slot
     int64_t slot_frames = 0, slot_groups = 0;
+    int slot_tiles = 0, slot_chains = 0;
     int64_t n_sb_total = 0;
     std::vector<char> fuse_kw;            // per track: K-weighting runs in the k_eq epilogue
+    std::vector<EqCfgTable> eq_tables;    // per k_eq launch: the coefficient sets of its tracks (passed as the kernel parameter)
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     int n_sm = 148, chain_warps = 0;      // see chain_threads()
     size_t ws_bytes = 0;
@@ -280,35 +291,64 @@ double eq_cost_per_frame(const ame_track_params &t) {
 constexpr double kEqCostKw = 30.0;                      // K-weighting epilogue: two sections + squares, two channels
 
 // k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
-// both variants one after the other.  Every track therefore gets a whole number of warps, in proportion to its
-// cost (frames x cost per frame), and its 32 * warps jobs are spread over its chunks by length.
-std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<double> &cost,
-                                    int t_lo, int t_hi, int64_t slots, const std::vector<int64_t> &min_tiles) {
-    const int n = (int)chunks.size();
-    std::vector<int> warps(n, 0);
-    std::vector<double> weight(n, 0.0);
-    std::vector<int> cap(n, 0);
-    double wsum = 0;
+// both variants one after the other: every track gets a whole number of warps.  A thread's time is about
+// (tile + warm-up) * cost per frame, and both the cost (no EQ at all ... 4 stages + warmth + K-weighting) and the
+// warm-up (0 ... EQ + K filter) differ a lot between tracks: give every track the tile length that makes that
+// product equal to one common budget, the smallest budget whose job count fits `slots` threads.
+struct EqTrack { double cost; int64_t warm, min_tile, q; };
+
+int64_t eq_jobs_of_track(const std::vector<int64_t> &chunks, int64_t T) {
+    int64_t jobs = 0;
+    for (int64_t cn : chunks) jobs += (cn + T - 1) / T;
+    return (jobs + 31) / 32 * 32;
+}
+
+std::vector<int64_t> eq_tiles_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<EqTrack> &et,
+                                        int t_lo, int t_hi, int64_t slots) {
+    auto tile_of = [&](int t, double budget) {
+        const EqTrack &e = et[t];
+        int64_t T = (int64_t)(budget / e.cost) - e.warm;
+        T = T / e.q * e.q;
+        return std::max(T, e.min_tile);
+    };
+    auto total = [&](double budget) {
+        int64_t jobs = 0;
+        for (int t = t_lo; t < t_hi; ++t) jobs += eq_jobs_of_track(chunks[t], tile_of(t, budget));
+        return jobs;
+    };
+    double lo = 0.0, hi = 1.0;
     for (int t = t_lo; t < t_hi; ++t) {
-        int64_t frames = 0, max_jobs = 0;
-        for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tiles[t]); }
-        weight[t] = (double)frames * cost[t];
-        cap[t] = (int)std::max<int64_t>(1, (max_jobs + 31) / 32);
-        wsum += weight[t];
+        int64_t longest = 1;
+        for (int64_t cn : chunks[t]) longest = std::max(longest, cn);
+        hi = std::max(hi, (double)(longest + et[t].warm + et[t].q) * et[t].cost);
     }
-    int64_t avail = std::max<int64_t>(t_hi - t_lo, slots / 32);
-    std::vector<std::pair<double, int>> rem;
-    int64_t used = 0;
-    for (int t = t_lo; t < t_hi; ++t) {
-        const double share = wsum > 0 ? avail * weight[t] / wsum : 1.0;
-        warps[t] = std::min(cap[t], std::max(1, (int)share));
-        used += warps[t];
-        rem.emplace_back(share - warps[t], t);
+    if (total(lo) > slots)
+        for (int it = 0; it < 60; ++it) {        // total() is non-increasing in the budget
+            const double mid = 0.5 * (lo + hi);
+            if (total(mid) <= slots) hi = mid; else lo = mid;
+        }
+    else hi = lo;
+    std::vector<int64_t> T(chunks.size(), 0);
+    for (int t = t_lo; t < t_hi; ++t) T[t] = tile_of(t, hi);
+    return T;
+}
+
+EqCfg eq_cfg_of(const ame_track_params &t) {
+    EqCfg c;
+    std::memset(&c, 0, sizeof c);
+    c.wl_b0 = t.wl_b0; c.wl_b1 = t.wl_b1; c.wl_a1 = t.wl_a1; c.wl_gm1 = t.wl_gm1;
+    c.wh_b0 = t.wh_b0; c.wh_b1 = t.wh_b1; c.wh_a1 = t.wh_a1; c.wh_gm1 = t.wh_gm1;
+    c.s0_b0 = t.eq[0].s[0].b0; c.s0_a1 = t.eq[0].s[0].a1; c.s0_a2 = t.eq[0].s[0].a2; c.g0 = t.eq[0].g; c.gm0 = t.eq[0].gm1;
+    c.p1_b0 = t.eq[1].s[0].b0; c.gm1 = t.eq[1].gm1;
+    c.p2_b0 = t.eq[2].s[0].b0; c.gm2 = t.eq[2].gm1;
+    for (int i = 0; i < 4; ++i) {
+        c.p1_a1[i] = t.eq[1].s[i].a1; c.p1_a2[i] = t.eq[1].s[i].a2;
+        c.p2_a1[i] = t.eq[2].s[i].a1; c.p2_a2[i] = t.eq[2].s[i].a2;
     }
-    std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
-    for (size_t i = 0; i < rem.size() && used < avail; ++i)
-        if (warps[rem[i].second] < cap[rem[i].second]) { ++warps[rem[i].second]; ++used; }
-    return warps;
+    c.s3_b0 = t.eq[3].s[0].b0; c.s3_a1 = t.eq[3].s[0].a1; c.s3_a2 = t.eq[3].s[0].a2; c.g3 = t.eq[3].g; c.gm3 = t.eq[3].gm1;
+    c.k0b0 = t.kw[0].b0; c.k0b1 = t.kw[0].b1; c.k0b2 = t.kw[0].b2; c.k0a1 = t.kw[0].a1; c.k0a2 = t.kw[0].a2;
+    c.k1a1 = t.kw[1].a1; c.k1a2 = t.kw[1].a2;
+    return c;
 }
 
 int validate(const ame_track_params &t, int idx) {
@@ -397,7 +437,8 @@ int check_warmth(const ame_plan *p) {
 struct Bufs {
     const int16_t *in = nullptr;
     int16_t *pre = nullptr, *bands = nullptr, *out = nullptr;
-    uint16_t *rms = nullptr;
+    uint16_t *rms = nullptr, *list = nullptr;
+    int *tile_cnt = nullptr, *n_flagged = nullptr;
     GrpRec *grp = nullptr;
     double *att = nullptr;
     int64_t *hist = nullptr;
@@ -408,7 +449,8 @@ Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) 
     Bufs b;
     b.in = d_in; b.out = d_out;
     b.pre = sl.pre - 2 * w.frame_lo;
-    b.bands = sl.bands; b.rms = sl.rms; b.grp = sl.grp; b.att = sl.att;
+    b.bands = sl.bands; b.rms = sl.rms; b.list = sl.list; b.tile_cnt = sl.tile_cnt; b.n_flagged = sl.n_flagged;
+    b.grp = sl.grp; b.att = sl.att;
     b.hist = (int64_t *)p->d_hist;
     return b;
 }
@@ -418,9 +460,18 @@ int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cuda
     if (nt > 0) CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));   // k_eq's K-weighting epilogue feeds it
     if (!w.eq_n) return AME_OK;
     t_begin(p, S_EQ, s);
-    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_tdev, p->d_luts, d_in, d_pre,
-                                              p->d_energy, p->d_peak);
-    LAUNCH_CHECK(p);
+    for (const Wave::EqLaunch &g : w.eq_launches) {
+        if (g.plain) {
+            k_eq<<<(g.job_n + 127) / 128, 128, 0, s>>>(p->eq_tables[g.table], p->d_eq_jobs + g.job_lo, g.job_n, p->d_tracks, p->d_tdev,
+                                                       p->d_luts, d_in, d_pre, p->d_energy, p->d_peak);
+            LAUNCH_CHECK(p);
+        }
+        if (g.fused) {
+            k_eq_kw<<<(g.job_n + 127) / 128, 128, 0, s>>>(p->eq_tables[g.table], p->d_eq_jobs + g.job_lo, g.job_n, p->d_tracks,
+                                                          p->d_tdev, p->d_luts, d_in, d_pre, p->d_energy, p->d_peak);
+            LAUNCH_CHECK(p);
+        }
+    }
     t_end(p, S_EQ, s);
     return AME_OK;
 }
@@ -428,8 +479,12 @@ int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cuda
 int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands, cudaStream_t s) {
     if (!w.split_n) return AME_OK;
     t_begin(p, S_SPLIT, s);
-    k_band_split<<<(w.split_n + 127) / 128, 128, 0, s>>>(p->d_split_jobs + w.split_lo, w.split_n, p->d_tracks, p->d_mb_delta,
-                                                         d_pre, d_bands, p->mb_frames);
+    if (w.xover_uni)
+        k_band_split<true><<<(w.split_n + 127) / 128, 128, 0, s>>>(w.xover, p->d_split_jobs + w.split_lo, w.split_n, p->d_tracks, p->d_mb_delta,
+                                                                   d_pre, d_bands, p->mb_frames);
+    else
+        k_band_split<false><<<(w.split_n + 127) / 128, 128, 0, s>>>(w.xover, p->d_split_jobs + w.split_lo, w.split_n, p->d_tracks, p->d_mb_delta,
+                                                                    d_pre, d_bands, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_SPLIT, s);
     return AME_OK;
@@ -439,7 +494,7 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
 // a segment is shorter than the distance after which trajectories meet; the pass cost is so low on the dense list
 // that 4 warps are right from one track to the full batch, 8 when only a few chains share the machine.
 int chain_lanes(const ame_plan *p, int n_chains) {
-    if (p->chain_warps < 0) return 1;                       // the sequential loop, one lane per chain
+    if (p->chain_warps < 0) return 1;                       // ONE lane per chain: the sequential loop
     if (p->chain_warps > 0) return 32 * p->chain_warps;
     return n_chains * 2 <= p->n_sm ? 256 : 128;
 }
@@ -447,13 +502,16 @@ int chain_lanes(const ame_plan *p, int n_chains) {
 int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     if (!w.chain_n) return AME_OK;
     t_begin(p, S_FLAG, s);
-    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, b.bands, b.rms, p->mb_frames);
+    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, b.bands, b.rms, p->mb_frames, b.tile_cnt);
+    LAUNCH_CHECK(p);
+    k_compact<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, w.chain_lo, b.rms, b.tile_cnt, b.list, b.grp,
+                                            b.n_flagged, p->mb_frames);
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
     const int lanes = chain_lanes(p, w.chain_n);
-    k_att_chain<<<w.chain_n, std::max(lanes, 128), 0, s>>>(p->d_chain_jobs + w.chain_lo, b.rms, p->d_tables, b.grp, b.att, p->mb_frames,
-                                                           lanes, p->d_chain_stats + 2 * (size_t)w.chain_lo);
+    k_att_chain<<<w.chain_n, std::max(lanes, 32), 0, s>>>(p->d_chain_jobs + w.chain_lo, b.list, b.n_flagged, p->d_tables, b.att, p->mb_frames,
+                                            lanes, p->d_chain_stats + 2 * (size_t)w.chain_lo);
     LAUNCH_CHECK(p);
     t_end(p, S_CHAIN, s);
     t_begin(p, S_APPLY, s);
@@ -469,7 +527,12 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     if (nt <= 0) return AME_OK;
     if (w.kw_n) {
         t_begin(p, S_KW, s);
-        k_kweight_energy<<<(w.kw_n + 127) / 128, 128, 0, s>>>(p->d_kw_jobs + w.kw_lo, w.kw_n, p->d_tracks, p->d_tdev, d_pre, p->d_energy, p->d_peak);
+        if (w.kw_uni)
+            k_kweight_energy<true><<<(w.kw_n + 127) / 128, 128, 0, s>>>(w.kw, p->d_kw_jobs + w.kw_lo, w.kw_n, p->d_tracks, p->d_tdev, d_pre,
+                                                                        p->d_energy, p->d_peak);
+        else
+            k_kweight_energy<false><<<(w.kw_n + 127) / 128, 128, 0, s>>>(w.kw, p->d_kw_jobs + w.kw_lo, w.kw_n, p->d_tracks, p->d_tdev, d_pre,
+                                                                         p->d_energy, p->d_peak);
         LAUNCH_CHECK(p);
         t_end(p, S_KW, s);
     }
@@ -549,7 +612,9 @@ void ame_plan_destroy(ame_plan *p) {
     cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
     for (void *q : ptrs) dev_free(q);
     for (Slot &sl : p->slots) {
-        for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.grp, (void *)sl.att}) dev_free(q);
+        for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.list, (void *)sl.tile_cnt, (void *)sl.n_flagged,
+                        (void *)sl.grp, (void *)sl.att})
+            dev_free(q);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     for (cudaStream_t s : {p->s_in, p->s_out})
@@ -608,9 +673,11 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         // be the 1 -2 1 the kernel hard-wires
         const int64_t cf = tp.chunk_frames;
         const bool one_chunk = cf <= 0 || tp.n_frames <= cf;
-        p->fuse_kw[t] = o.fuse_kw >= 0 && !(tp.flags & AME_F_MULTIBAND) && tp.halo_frames == 0 && s100 >= 8 &&
+        p->fuse_kw[t] = o.fuse_kw > 0 && !(tp.flags & AME_F_MULTIBAND) && tp.halo_frames == 0 && s100 >= 8 &&
                         (one_chunk || cf % s100 == 0) && tp.kw[1].b0 == 1.0 && tp.kw[1].b1 == -2.0 && tp.kw[1].b2 == 1.0;
         p->tdev[t].fused = p->fuse_kw[t];
+        p->tdev[t].eq_cfg = 0;
+        p->tdev[t].pad = 0;
     }
     for (size_t i = 1; i < spans.size(); ++i)
         if (spans[i].first < align_up(spans[i - 1].second, 8)) return bail(fail(AME_E_INVALID, "tracks overlap in the packed buffer"));
@@ -677,21 +744,28 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     p->n_sm = n_sm;
     p->chain_warps = std::max(-1, std::min(o.chain_warps, kChainMaxThreads / 32));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split<true>, 128, 0);
+    if (const char *e = std::getenv("AME_EQ_CTAS_PER_SM")) occ_eq = std::max(1, std::atoi(e));       // experiments
+    if (const char *e = std::getenv("AME_SPLIT_CTAS_PER_SM")) occ_split = std::max(1, std::atoi(e));
     const int share = std::min(n_slots, 4);
     const int64_t eq_slots = (int64_t)n_sm * std::max(occ_eq, 1) * 128 / share;         // one thread per tile
     const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128 / share;
     constexpr int64_t kMinTile = 512;
     int64_t split_tile = kMinTile;
-    std::vector<double> eq_cost(n_tracks);
-    std::vector<int64_t> eq_min_tile(n_tracks, kMinTile);
-    std::vector<int> eq_warps(n_tracks, 1);
+    std::vector<EqTrack> eq_track(n_tracks);
+    std::vector<int64_t> eq_tile_of(n_tracks, kMinTile);
     int max_warm_kw = 0, min_s100 = 1 << 30;
     int64_t n_sb_kw = 0;                                  // sub-blocks left to k_kweight_energy
     for (int t = 0; t < n_tracks; ++t) {
-        eq_cost[t] = eq_cost_per_frame(p->tracks[t]) + (p->fuse_kw[t] ? kEqCostKw : 0.0);
-        if (p->fuse_kw[t]) eq_min_tile[t] = p->tdev[t].s100;
-        else {
+        const ame_track_params &tp = p->tracks[t];
+        bool any_eq = false;
+        for (int s = 0; s < 4; ++s) any_eq = any_eq || tp.eq[s].kind != AME_EQ_BYPASS;
+        EqTrack &e = eq_track[t];
+        e.cost = eq_cost_per_frame(tp) + (p->fuse_kw[t] ? kEqCostKw : 0.0);
+        e.warm = (any_eq ? tp.warm_eq : 0) + (p->fuse_kw[t] ? tp.warm_kw : 0);
+        e.q = p->fuse_kw[t] ? p->tdev[t].s100 : 8;
+        e.min_tile = p->fuse_kw[t] ? p->tdev[t].s100 : kMinTile;
+        if (!p->fuse_kw[t]) {
             n_sb_kw += p->tdev[t].n_sb;
             max_warm_kw = std::max(max_warm_kw, p->tracks[t].warm_kw);
             min_s100 = std::min(min_s100, p->tdev[t].s100);
@@ -702,8 +776,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         for (int t = wv.track_lo; t < wv.track_hi; ++t)
             if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
         split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
-        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, eq_min_tile);
-        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
+        const std::vector<int64_t> tt = eq_tiles_per_track(chunks_all, eq_track, wv.track_lo, wv.track_hi, eq_slots);
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_tile_of[t] = tt[t];
     }
     p->eq_tile = 0;
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
@@ -736,8 +810,33 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chunk_lo = (int)mb_chunks.size(); wv.kw_lo = (int)kw_jobs.size(); wv.gain_lo = (int)gain_jobs.size();
         wv.seg_lo = n_seg_total;
         int64_t n_groups = 0;                          // group records of this wave (slot-local indices)
+        std::map<std::string, int> cfg_index;          // coefficient sets of the current k_eq launch
+        p->eq_tables.emplace_back();
+        std::memset(&p->eq_tables.back(), 0, sizeof(EqCfgTable));
+        wv.eq_launches.push_back(Wave::EqLaunch{(int)eq_jobs.size(), 0, (int)p->eq_tables.size() - 1, false, false});
         for (int t = wv.track_lo; t < wv.track_hi; ++t) {
             ame_track_params &tp = p->tracks[t];
+            {
+                const EqCfg cfg = eq_cfg_of(tp);
+                const std::string key((const char *)&cfg, sizeof cfg);
+                auto it = cfg_index.find(key);
+                if (it == cfg_index.end()) {
+                    if ((int)cfg_index.size() == kMaxEqCfg) {          // table full: this track starts the next launch
+                        wv.eq_launches.back().job_n = (int)eq_jobs.size() - wv.eq_launches.back().job_lo;
+                        cfg_index.clear();
+                        p->eq_tables.emplace_back();
+                        std::memset(&p->eq_tables.back(), 0, sizeof(EqCfgTable));
+                        wv.eq_launches.push_back(Wave::EqLaunch{(int)eq_jobs.size(), 0, (int)p->eq_tables.size() - 1, false, false});
+                    }
+                    const int idx = (int)cfg_index.size();
+                    cfg_index[key] = idx;
+                    p->eq_tables.back().c[idx] = cfg;
+                    p->tdev[t].eq_cfg = idx;
+                } else {
+                    p->tdev[t].eq_cfg = it->second;
+                }
+                (p->fuse_kw[t] ? wv.eq_launches.back().fused : wv.eq_launches.back().plain) = true;
+            }
             int variant = 0;
             for (int s = 0; s < 4; ++s)
                 if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
@@ -765,17 +864,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             const size_t eq_first = eq_jobs.size();
             {
                 int64_t c0e = 0;
-                const int64_t want = (int64_t)eq_warps[t] * 32;
-                const int64_t q = p->fuse_kw[t] ? p->tdev[t].s100 : 8;
+                const int64_t q = eq_track[t].q;
                 for (int64_t cn : chunks_all[t]) {
                     const int64_t cb = tp.offset_frames + tp.halo_frames + c0e, ce = cb + cn;
-                    int64_t T;
-                    if (o.eq_tile_frames > 0) {
-                        T = align_up(o.eq_tile_frames, q);
-                    } else {
-                        const int64_t jc = std::max<int64_t>(1, want * cn / std::max<int64_t>(tp.n_frames, 1));   // floor: never over `want`
-                        T = std::max<int64_t>(eq_min_tile[t], align_up((cn + jc - 1) / jc, q));
-                    }
+                    const int64_t T = o.eq_tile_frames > 0 ? align_up(o.eq_tile_frames, q) : eq_tile_of[t];
                     if (p->fuse_kw[t]) tile_jobs_grid(eq_jobs, t, variant, cb, ce, T, q);
                     else tile_jobs(eq_jobs, t, variant, cb, ce, T);
                     p->eq_tile = std::max<int>(p->eq_tile, (int)std::min<int64_t>(T, INT32_MAX));
@@ -798,7 +890,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                         const double thr = tp.comp[b].thresh_rms;
                         const uint32_t thr_i = thr >= 65535.0 ? 0x7fffffffu : (uint32_t)std::floor(thr) + 1u;
                         ck.grp_begin[b] = n_groups;
-                        chain_jobs.push_back(ChainJob{ck.mb_begin, cn, n_groups, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames});
+                        chain_jobs.push_back(ChainJob{ck.mb_begin, cn, n_groups, b, tp.comp[b].table, thr_i, tp.comp[b].look_frames, 0, 0});
                         n_groups += (cn + 31) / 32;
                     }
                     n_seg_total += (cn + kSeg - 1) / kSeg;
@@ -813,17 +905,42 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                 gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
                                             tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
         }
+        wv.eq_launches.back().job_n = (int)eq_jobs.size() - wv.eq_launches.back().job_lo;
+        {
+            bool have_x = false, have_k = false;
+            wv.xover_uni = wv.kw_uni = true;
+            for (int t = wv.track_lo; t < wv.track_hi; ++t) {
+                const ame_track_params &tp = p->tracks[t];
+                if (tp.flags & AME_F_MULTIBAND) {
+                    const XoverCfg x{tp.xlp[0].b0, tp.xlp[0].a1, tp.xlp[0].a2, tp.xlp[1].a1, tp.xlp[1].a2,
+                                     tp.xhp[0].b0, tp.xhp[0].a1, tp.xhp[0].a2, tp.xhp[1].a1, tp.xhp[1].a2};
+                    if (!have_x) { wv.xover = x; have_x = true; }
+                    else if (std::memcmp(&x, &wv.xover, sizeof x)) wv.xover_uni = false;
+                }
+                if (!p->fuse_kw[t]) {
+                    const KwCfg k{tp.kw[0].b0, tp.kw[0].b1, tp.kw[0].b2, tp.kw[0].a1, tp.kw[0].a2, tp.kw[1].a1, tp.kw[1].a2};
+                    const bool rlb = tp.kw[1].b0 == 1.0 && tp.kw[1].b1 == -2.0 && tp.kw[1].b2 == 1.0;
+                    if (!have_k) { wv.kw = k; have_k = true; }
+                    else if (std::memcmp(&k, &wv.kw, sizeof k)) wv.kw_uni = false;
+                    if (!rlb) wv.kw_uni = false;
+                }
+            }
+        }
         wv.n_groups = n_groups;
         p->slot_groups = std::max(p->slot_groups, n_groups);
         // longest chains first inside the wave: the launch ends with its slowest CTA
         std::stable_sort(chain_jobs.begin() + wv.chain_lo, chain_jobs.end(), [](const ChainJob &a, const ChainJob &b) { return a.n > b.n; });
         wv.wf_lo = (int)wf_jobs.size();
-        for (int c = wv.chain_lo; c < (int)chain_jobs.size(); ++c)
+        for (int c = wv.chain_lo; c < (int)chain_jobs.size(); ++c) {
+            chain_jobs[c].tile0 = (int)wf_jobs.size() - wv.wf_lo;
             for (int64_t tb = 0; tb < chain_jobs[c].n; tb += kWfTile) wf_jobs.push_back(WfJob{c, 0, tb});
+        }
         wv.eq_n = (int)eq_jobs.size() - wv.eq_lo; wv.split_n = (int)split_jobs.size() - wv.split_lo;
         wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
         wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
         wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
+        p->slot_tiles = std::max(p->slot_tiles, wv.wf_n);
+        p->slot_chains = std::max(p->slot_chains, wv.chain_n);
     }
 
     // ---- device state -------------------------------------------------------------------------
@@ -838,6 +955,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         if ((rc = dmalloc(p, (void **)&sl.pre, (size_t)p->slot_frames * 4)) ||
             (rc = dmalloc(p, (void **)&sl.bands, (size_t)p->mb_frames * 4 * 3)) ||
             (rc = dmalloc(p, (void **)&sl.rms, (size_t)p->mb_frames * 2 * 3)) ||
+            (rc = dmalloc(p, (void **)&sl.list, (size_t)p->mb_frames * 2 * 3)) ||
+            (rc = dmalloc(p, (void **)&sl.tile_cnt, (size_t)std::max(p->slot_tiles, 1) * sizeof(int))) ||
+            (rc = dmalloc(p, (void **)&sl.n_flagged, (size_t)std::max(p->slot_chains, 1) * sizeof(int))) ||
             (rc = dmalloc(p, (void **)&sl.grp, (size_t)p->slot_groups * sizeof(GrpRec))) ||
             (rc = dmalloc(p, (void **)&sl.att, (size_t)p->mb_frames * 8 * 3)))
             return bail(rc);

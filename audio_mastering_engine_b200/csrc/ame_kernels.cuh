@@ -35,6 +35,8 @@ struct ChainJob {          // one warp of k_compress: one band of one chunk of a
     int32_t table;
     uint32_t thr_i;        // rms > thresh_rms  <=>  rms >= thr_i
     int32_t look;          // look_frames
+    int32_t tile0;         // index (within the wave's launch) of the chain's first k_window_flag / k_compact tile
+    int32_t pad;
 };
 
 struct KwJob { int32_t track; int32_t sb_begin; int32_t sb_end; int32_t pad; };
@@ -51,8 +53,24 @@ struct TrackDev {          // device-side per-track bookkeeping
     int32_t s100;          // frames per 100 ms = (fs + 5) / 10   (ebur128.c)
     int32_t first_block;   // time shards: 400 ms blocks before this one belong to the previous shard / the warm-up
     int32_t fused;         // K-weighting runs in the k_eq epilogue (no k_kweight_energy jobs)
+    int32_t eq_cfg;        // index of the track's EqCfg in the table of its k_eq launch
+    int32_t pad;
     int64_t n_total;       // halo + span frames
 };
+
+// Everything k_eq needs that is the same for every tile of a track.  The table of the configurations of one launch is
+// a KERNEL PARAMETER (constant bank) and the warp's index into it is warp-uniform, so the compiler keeps the
+// coefficients in uniform registers (DFMA takes a UR operand) instead of ~90 of the 255 vector registers a thread has.
+struct EqCfg {
+    double wl_b0, wl_b1, wl_a1, wl_gm1, wh_b0, wh_b1, wh_a1, wh_gm1;      // warmth (:258-266)
+    double s0_b0, s0_a1, s0_a2, g0, gm0;                                  // low shelf 250 Hz
+    double p1_b0, p1_a1[4], p1_a2[4], gm1;                                // peak 1 kHz (4 sections, unit gain but the first)
+    double p2_b0, p2_a1[4], p2_a2[4], gm2;                                // peak 4 kHz
+    double s3_b0, s3_a1, s3_a2, g3, gm3;                                  // high shelf 8 kHz
+    double k0b0, k0b1, k0b2, k0a1, k0a2, k1a1, k1a2;                      // K-weighting (pre-filter; RLB denominators)
+};
+constexpr int kMaxEqCfg = 88;                                            // 88 * 360 B + the other parameters < 32764 B
+struct EqCfgTable { EqCfg c[kMaxEqCfg]; };
 
 __constant__ double c_hist_bounds[1001];
 __constant__ double c_hist_energy[1000];
@@ -123,17 +141,12 @@ __device__ __forceinline__ double shelf_cut(double v, double f, double g) {
     return __dadd_rn(t, __dsub_rn(f, t));
 }
 
-struct PeakCoef { double b0, a1[4], a2[4]; };     // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
-__device__ __forceinline__ void load_peak(PeakCoef &c, const ame_eq_stage &st) {
-    c.b0 = st.s[0].b0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { c.a1[i] = st.s[i].a1; c.a2[i] = st.s[i].a2; }
-}
-__device__ __forceinline__ double peak_step(const PeakCoef &c, double *z, double x) {
-    double t = bw_step<1>(c.b0, c.a1[0], c.a2[0], z[0], z[1], x);
-    t = bw_step1<1>(c.a1[1], c.a2[1], z[2], z[3], t);
-    t = bw_step1<-1>(c.a1[2], c.a2[2], z[4], z[5], t);
-    return bw_step1<-1>(c.a1[3], c.a2[3], z[6], z[7], t);
+// butter(4, bandpass, sos): numerator signs (+,+,-,-), sections 1..3 of unit gain
+__device__ __forceinline__ double peak_step(double b0, const double *a1, const double *a2, double *z, double x) {
+    double t = bw_step<1>(b0, a1[0], a2[0], z[0], z[1], x);
+    t = bw_step1<1>(a1[1], a2[1], z[2], z[3], t);
+    t = bw_step1<-1>(a1[2], a2[2], z[4], z[5], t);
+    return bw_step1<-1>(a1[3], a2[3], z[6], z[7], t);
 }
 
 // exact int16 -> x / 32768 as double in ONE add: bits of 2^37 + (x + 2^31) * 2^-15, minus 2^37 + 2^16
@@ -153,30 +166,15 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 // whole track while the EQ restarts with every chunk, the EQ state is reset when the walk crosses a chunk start.
 // ------------------------------------------------------------------------------------------------
 template <int MASK, bool WARM, bool KW>
-__device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp, const TrackDev *__restrict__ tdp,
-                                        const double *__restrict__ luts, const int16_t *__restrict__ in,
-                                        int16_t *__restrict__ pre, double *__restrict__ energy, int *__restrict__ peak) {
+__device__ __forceinline__ void eq_tile(const TileJob &job, const EqCfg &c, const ame_track_params *__restrict__ tp,
+                                        const TrackDev *__restrict__ tdp, const double *__restrict__ luts,
+                                        const int16_t *__restrict__ in, int16_t *__restrict__ pre,
+                                        double *__restrict__ energy, int *__restrict__ peak) {
     const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
     const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
-    double wl_b0 = 0, wl_b1 = 0, wl_a1 = 0, wl_gm1 = 0, wh_b0 = 0, wh_b1 = 0, wh_a1 = 0, wh_gm1 = 0;
-    if (WARM) {
-        wl_b0 = tp->wl_b0; wl_b1 = tp->wl_b1; wl_a1 = tp->wl_a1; wl_gm1 = tp->wl_gm1;
-        wh_b0 = tp->wh_b0; wh_b1 = tp->wh_b1; wh_a1 = tp->wh_a1; wh_gm1 = tp->wh_gm1;
-    }
-    double s0_b0 = 0, s0_a1 = 0, s0_a2 = 0, g0 = 0, gm0 = 0, s3_b0 = 0, s3_a1 = 0, s3_a2 = 0, g3 = 0, gm3 = 0, gm1 = 0, gm2 = 0;
-    bool boost0 = false, boost3 = false;
-    PeakCoef p1, p2;
-    if (MASK & 1) {
-        s0_b0 = tp->eq[0].s[0].b0; s0_a1 = tp->eq[0].s[0].a1; s0_a2 = tp->eq[0].s[0].a2;
-        g0 = tp->eq[0].g; gm0 = tp->eq[0].gm1; boost0 = tp->eq[0].kind == AME_EQ_SHELF_BOOST;
-    }
-    if (MASK & 2) { load_peak(p1, tp->eq[1]); gm1 = tp->eq[1].gm1; }
-    if (MASK & 4) { load_peak(p2, tp->eq[2]); gm2 = tp->eq[2].gm1; }
-    if (MASK & 8) {
-        s3_b0 = tp->eq[3].s[0].b0; s3_a1 = tp->eq[3].s[0].a1; s3_a2 = tp->eq[3].s[0].a2;
-        g3 = tp->eq[3].g; gm3 = tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
-    }
+    const bool boost0 = (MASK & 1) && tp->eq[0].kind == AME_EQ_SHELF_BOOST;
+    const bool boost3 = (MASK & 8) && tp->eq[3].kind == AME_EQ_SHELF_BOOST;
     double zl[20], zr[20];
 #pragma unroll
     for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
@@ -185,7 +183,6 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     int64_t f_lo, zero_before, next_reset = INT64_MAX;
     const int64_t cf = tp->chunk_frames > 0 ? (int64_t)tp->chunk_frames : INT64_MAX / 4;
     // K-weighting state (BS.1770 pre-filter: general biquad; RLB high-pass: numerator exactly 1 -2 1)
-    double k0b0 = 0, k0b1 = 0, k0b2 = 0, k0a1 = 0, k0a2 = 0, k1a1 = 0, k1a2 = 0;
     double kzl[4] = {0, 0, 0, 0}, kzr[4] = {0, 0, 0, 0}, accl = 0, accr = 0;
     int pk = 0, sb = 0, n_sb = 0, s100 = 1, left = 1;
     int64_t sb_off = 0;
@@ -196,8 +193,6 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         if (f_lo < track_begin) f_lo = track_begin;
         zero_before = track_begin;
         next_reset = track_begin + ((f_lo - track_begin) / cf + 1) * cf;     // first chunk start after f_lo
-        k0b0 = tp->kw[0].b0; k0b1 = tp->kw[0].b1; k0b2 = tp->kw[0].b2; k0a1 = tp->kw[0].a1; k0a2 = tp->kw[0].a2;
-        k1a1 = tp->kw[1].a1; k1a2 = tp->kw[1].a2;
         const TrackDev td = *tdp;
         s100 = td.s100; n_sb = td.n_sb; sb_off = td.sb_offset;
         sb = (int)((job.tile_begin - track_begin) / s100);  // tiles of this path start on the sub-block grid
@@ -214,14 +209,14 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
 
     auto cascade = [&](double v, double *z) -> float {     // one channel through the 4 EQ stages
         if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
-            const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
-            v = boost0 ? v + (f - v) * gm0 : shelf_cut<true>(v, f, g0);
+            const double f = bw_step<1>(c.s0_b0, c.s0_a1, c.s0_a2, z[0], z[1], v);
+            v = boost0 ? v + (f - v) * c.gm0 : shelf_cut<true>(v, f, c.g0);
         }
-        if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
-        if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
+        if (MASK & 2) v = v + peak_step(c.p1_b0, c.p1_a1, c.p1_a2, z + 2, v) * c.gm1;    // apply_peak_filter 1 kHz (:290-298)
+        if (MASK & 4) v = v + peak_step(c.p2_b0, c.p2_a1, c.p2_a2, z + 10, v) * c.gm2;   // apply_peak_filter 4 kHz
         if (MASK & 8) {   // apply_shelf_filter 8 kHz high
-            const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
-            v = boost3 ? v + (f - v) * gm3 : shelf_cut<(MASK & 7) == 0>(v, f, g3);
+            const double f = bw_step<-1>(c.s3_b0, c.s3_a1, c.s3_a2, z[18], z[19], v);
+            v = boost3 ? v + (f - v) * c.gm3 : shelf_cut<(MASK & 7) == 0>(v, f, c.g3);
         }
         return __double2float_rn(v);                       // samples[:, i] = ... into the float32 array (:274)
     };
@@ -239,14 +234,14 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
             // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels:
             //   y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y - x)*(g - 1)       (no FMA contraction)
             double L = lutL, R = lutR;
-            double y0 = __dmul_rn(wl_b0, L);
-            double y1 = __dadd_rn(__dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0)), __dmul_rn(wl_b0, R));
-            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), wl_gm1));
-            const double R1 = __dadd_rn(R, __dmul_rn(__dsub_rn(y1, R), wl_gm1));
-            y0 = __dmul_rn(wh_b0, L1);
-            y1 = __dadd_rn(__dsub_rn(__dmul_rn(wh_b1, L1), __dmul_rn(wh_a1, y0)), __dmul_rn(wh_b0, R1));
-            L = __dadd_rn(L1, __dmul_rn(__dsub_rn(y0, L1), wh_gm1));
-            R = __dadd_rn(R1, __dmul_rn(__dsub_rn(y1, R1), wh_gm1));
+            double y0 = __dmul_rn(c.wl_b0, L);
+            double y1 = __dadd_rn(__dsub_rn(__dmul_rn(c.wl_b1, L), __dmul_rn(c.wl_a1, y0)), __dmul_rn(c.wl_b0, R));
+            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), c.wl_gm1));
+            const double R1 = __dadd_rn(R, __dmul_rn(__dsub_rn(y1, R), c.wl_gm1));
+            y0 = __dmul_rn(c.wh_b0, L1);
+            y1 = __dadd_rn(__dsub_rn(__dmul_rn(c.wh_b1, L1), __dmul_rn(c.wh_a1, y0)), __dmul_rn(c.wh_b0, R1));
+            L = __dadd_rn(L1, __dmul_rn(__dsub_rn(y0, L1), c.wh_gm1));
+            R = __dadd_rn(R1, __dmul_rn(__dsub_rn(y1, R1), c.wh_gm1));
             xl = to_pcm_f64(L);                            // float_array_to_audio_segment (:254-257)
             xr = to_pcm_f64(R);
         }
@@ -268,8 +263,8 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         const int ol = to_pcm_f32(yl), orr = to_pcm_f32(yr);   // clip inside to_pcm == np.clip of (:270) then (:255)
         if (KW) {
             // ebur128 filter on x / 32768 (k_kweight_energy has the same arithmetic); energies only inside the tile
-            const double kl = bw_step1<-1>(k1a1, k1a2, kzl[2], kzl[3], kw_pre(k0b0, k0b1, k0b2, k0a1, k0a2, kzl[0], kzl[1], i16_to_unit(ol)));
-            const double kr = bw_step1<-1>(k1a1, k1a2, kzr[2], kzr[3], kw_pre(k0b0, k0b1, k0b2, k0a1, k0a2, kzr[0], kzr[1], i16_to_unit(orr)));
+            const double kl = bw_step1<-1>(c.k1a1, c.k1a2, kzl[2], kzl[3], kw_pre(c.k0b0, c.k0b1, c.k0b2, c.k0a1, c.k0a2, kzl[0], kzl[1], i16_to_unit(ol)));
+            const double kr = bw_step1<-1>(c.k1a1, c.k1a2, kzr[2], kzr[3], kw_pre(c.k0b0, c.k0b1, c.k0b2, c.k0a1, c.k0a2, kzr[0], kzr[1], i16_to_unit(orr)));
             if (f >= job.tile_begin && f < f_hi) {
                 pk = max(pk, max(abs(ol), abs(orr)));
                 if (sb < n_sb) {
@@ -327,43 +322,59 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     if (KW) atomicMax(peak + job.track, pk);
 }
 
-__global__ void __launch_bounds__(128, 2)
-k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks, const TrackDev *__restrict__ tdev,
-     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre,
-     double *__restrict__ energy, int *__restrict__ peak) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    const TileJob job = jobs[j];
-    if (job.tile_end <= job.tile_begin) return;           // padding job (tracks get whole warps)
-    const ame_track_params *tp = tracks + job.track;
-    const TrackDev *td = tdev + job.track;
-    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth, bit 5: K-weighting epilogue
-#define AME_EQ_CASE(M) case M: eq_tile<M, false, false>(job, tp, td, luts, in, pre, energy, peak); break; \
-                       case M + 16: eq_tile<M, true, false>(job, tp, td, luts, in, pre, energy, peak); break; \
-                       case M + 32: eq_tile<M, false, true>(job, tp, td, luts, in, pre, energy, peak); break; \
-                       case M + 48: eq_tile<M, true, true>(job, tp, td, luts, in, pre, energy, peak); break;
-        AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
-        AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
-        AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
-#undef AME_EQ_CASE
-    }
+// Two entry points over the same job list: k_eq takes the tracks whose K-weighting is a separate pass (3 CTAs per SM:
+// with the coefficients in uniform registers the full cascade fits 168 vector registers), k_eq_kw the tracks that
+// measure in the epilogue (2 CTAs per SM).  A warp whose track belongs to the other kernel leaves at once.
+#define AME_EQ_KERNEL(NAME, KWF, MIN_CTAS)                                                                              \
+__global__ void __launch_bounds__(128, MIN_CTAS)                                                                        \
+NAME(const __grid_constant__ EqCfgTable tab, const TileJob *__restrict__ jobs, int n_jobs,                              \
+     const ame_track_params *__restrict__ tracks, const TrackDev *__restrict__ tdev, const double *__restrict__ luts,  \
+     const int16_t *__restrict__ in, int16_t *__restrict__ pre, double *__restrict__ energy, int *__restrict__ peak) { \
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;                                                                \
+    if (j >= n_jobs) return;              /* whole warps: every track's jobs are padded to a multiple of 32 */         \
+    const TileJob job = jobs[j];                                                                                        \
+    const TrackDev *td = tdev + job.track;                                                                              \
+    /* a warp's 32 jobs belong to ONE track: its configuration index is warp-uniform, provably so after the shuffle */ \
+    const int cfg = __shfl_sync(kFull, td->eq_cfg, 0);                                                                  \
+    if (job.tile_end <= job.tile_begin || ((job.variant & 32) != 0) != KWF) return;   /* padding / the other kernel's */ \
+    const ame_track_params *tp = tracks + job.track;                                                                    \
+    const EqCfg &c = tab.c[cfg];                                                                                        \
+    switch (job.variant & 31) {           /* bits 0-3: EQ stages, bit 4: warmth */                                      \
+        AME_EQ_CASE(0, KWF) AME_EQ_CASE(1, KWF) AME_EQ_CASE(2, KWF) AME_EQ_CASE(3, KWF) AME_EQ_CASE(4, KWF)             \
+        AME_EQ_CASE(5, KWF) AME_EQ_CASE(6, KWF) AME_EQ_CASE(7, KWF) AME_EQ_CASE(8, KWF) AME_EQ_CASE(9, KWF)             \
+        AME_EQ_CASE(10, KWF) AME_EQ_CASE(11, KWF) AME_EQ_CASE(12, KWF) AME_EQ_CASE(13, KWF) AME_EQ_CASE(14, KWF)        \
+        AME_EQ_CASE(15, KWF)                                                                                            \
+    }                                                                                                                   \
 }
+#define AME_EQ_CASE(M, KWF) case M: eq_tile<M, false, KWF>(job, c, tp, td, luts, in, pre, energy, peak); break;       \
+                            case M + 16: eq_tile<M, true, KWF>(job, c, tp, td, luts, in, pre, energy, peak); break;
+AME_EQ_KERNEL(k_eq, false, 3)
+AME_EQ_KERNEL(k_eq_kw, true, 2)
+#undef AME_EQ_CASE
+#undef AME_EQ_KERNEL
 
 // ------------------------------------------------------------------------------------------------
 // k_band_split: int16 pre -> Butterworth-4 LP 250 / HP 4k in FP64, mid = x - low - high, each band
 // truncated to int16 (apply_multiband_compressor :300-305).  One thread per tile, both channels, same
 // warm-up scheme.  bands = 3 planes of mb_frames frames each.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3)
-k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+struct XoverCfg { double lb0, la10, la20, la11, la21, hb0, ha10, ha20, ha11, ha21; };
+
+// UNI: every multiband track of the launch has the same crossover (same sample rate) - the usual case; the
+// coefficients then come from the kernel parameter and live in uniform registers.
+template <bool UNI>
+__global__ void __launch_bounds__(128, 4)
+k_band_split(const __grid_constant__ XoverCfg xc, const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
              const int64_t *__restrict__ mb_delta,   // per track: mb_offset - offset_frames
              const int16_t *__restrict__ pre, int16_t *__restrict__ bands, int64_t mb_frames) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     const TileJob job = jobs[j];
     const ame_track_params *tp = tracks + job.track;
-    const double lb0 = tp->xlp[0].b0, la10 = tp->xlp[0].a1, la20 = tp->xlp[0].a2, la11 = tp->xlp[1].a1, la21 = tp->xlp[1].a2;
-    const double hb0 = tp->xhp[0].b0, ha10 = tp->xhp[0].a1, ha20 = tp->xhp[0].a2, ha11 = tp->xhp[1].a1, ha21 = tp->xhp[1].a2;
+    const double lb0 = UNI ? xc.lb0 : tp->xlp[0].b0, la10 = UNI ? xc.la10 : tp->xlp[0].a1, la20 = UNI ? xc.la20 : tp->xlp[0].a2,
+                 la11 = UNI ? xc.la11 : tp->xlp[1].a1, la21 = UNI ? xc.la21 : tp->xlp[1].a2;
+    const double hb0 = UNI ? xc.hb0 : tp->xhp[0].b0, ha10 = UNI ? xc.ha10 : tp->xhp[0].a1, ha20 = UNI ? xc.ha20 : tp->xhp[0].a2,
+                 ha11 = UNI ? xc.ha11 : tp->xhp[1].a1, ha21 = UNI ? xc.ha21 : tp->xhp[1].a2;
     const int64_t delta = mb_delta[job.track];
     double zl[8], zr[8];
 #pragma unroll
@@ -429,15 +440,16 @@ k_band_split(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_param
 // Multiband compressor = pydub compress_dynamic_range per band (:306-308), split by what is sequential:
 //   k_window_flag    (time-parallel)  window rms of the previous look_frames frames; emits the integer rms
 //                                     for frames ABOVE threshold and 0 otherwise (2 B per band frame)
-//   k_att_chain      (one CTA per (chunk, band))
-//        phase 0: the CTA streams its rms plane once, coalesced, and COMPACTS the flagged frames in place into a
-//                 dense list of rms values; per 32-frame group it leaves a record {bit mask of flagged frames,
-//                 number of flagged frames before the group}.  Below threshold the reference never releases
-//                 (max_attenuation = 0 => dec = 0), so unflagged frames are no-ops of the recurrence.
-//        phase 1: the attenuation recurrence over the dense list, cut into S segments of EQUAL step count that are
-//                 walked in parallel from a guessed start and repaired until every segment starts from its
-//                 predecessor's true end (exact, see below); emits the attenuation after every flagged frame as a
-//                 dense list (coalescible, no wasted steps, no divergence on silent frames).
+//   k_compact        (time-parallel)  one CTA per tile of a chain: COMPACTS the flagged frames into the chain's dense
+//                                     list of rms values (rank = flagged frames of the chain's earlier tiles + a
+//                                     scan inside the tile) and leaves per 32-frame group a record {bit mask of
+//                                     flagged frames, number of flagged frames before the group}.  Below threshold
+//                                     the reference never releases (max_attenuation = 0 => dec = 0), so unflagged
+//                                     frames are no-ops of the recurrence.
+//   k_att_chain      (one CTA per (chunk, band))  the attenuation recurrence over the dense list, cut into S segments
+//                                     of EQUAL step count that are walked in parallel from a guessed start and
+//                                     repaired until every segment starts from its predecessor's true end (exact);
+//                                     emits the attenuation after every flagged frame as a dense list.
 //   k_compress_apply (time-parallel)  attenuation in force at frame i = list[base + popc(mask up to i) - 1] (0 before
 //                                     the first flagged frame of the chunk); gain = 10^(-att/20), audioop.mul,
 //                                     low.overlay(mid).overlay(high) (:309).
@@ -491,9 +503,11 @@ __device__ __forceinline__ unsigned isqrt_ratio(unsigned long long s, unsigned n
 
 __global__ void __launch_bounds__(kWfThreads)
 k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chains, const int16_t *__restrict__ bands,
-              uint16_t *__restrict__ rms, int64_t mb_frames) {
+              uint16_t *__restrict__ rms, int64_t mb_frames, int *__restrict__ tile_cnt) {
     __shared__ long long s_scan[kWfThreads / 32];
     __shared__ unsigned long long s_head[kWfThreads / 32];
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
     const WfJob job = jobs[blockIdx.x];
     const ChainJob cj = chains[job.chain];
     const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + (int64_t)cj.band * mb_frames + cj.mb_begin;
@@ -541,6 +555,7 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
     const unsigned long long thr2 = (unsigned long long)cj.thr_i * cj.thr_i;
     const bool never = cj.thr_i > 32768u;          // rms <= 32768 can never exceed it
     uint32_t o[4] = {0, 0, 0, 0};
+    int n_flag = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int64_t i = i0 + k;
@@ -549,8 +564,13 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
         unsigned r = 0;
         if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
             r = isqrt_ratio((unsigned long long)s, (unsigned)(2 * nfr));
+        n_flag += r != 0;              // thr_i >= 1, so a flagged frame has rms >= 1
         o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
     }
+    // flagged frames of the tile: k_compact turns the counts into each tile's rank in its chain
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_flag += __shfl_xor_sync(kFull, n_flag, d);
+    if (lane == 0 && n_flag) atomicAdd(&s_cnt, n_flag);
     if (i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(rp + i0) & 15) == 0)) {
         *reinterpret_cast<uint4 *>(rp + i0) = make_uint4(o[0], o[1], o[2], o[3]);
     } else {
@@ -558,6 +578,8 @@ k_window_flag(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chain
         for (int k = 0; k < 8; ++k)
             if (i0 + k < n) rp[i0 + k] = (uint16_t)(o[k >> 1] >> ((k & 1) * 16));
     }
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_cnt;
 }
 
 // att' = (att <= M) ? min(att + inc, M) : max(att - dec, 0), evaluated as
@@ -580,12 +602,9 @@ __device__ __forceinline__ double att_update(double att, double m, double inc, d
 // ------------------------------------------------------------------------------------------------
 // k_att_chain: the attenuation recurrence of one (chunk, band), exact, parallel in time.
 //
-// Phase 0 (all threads): compaction.  The CTA walks its rms plane in tiles of blockDim * 8 frames; every thread
-//   loads 8 rms values (one 16-byte load), a CTA-wide exclusive scan of the flagged counts gives each flagged frame
-//   its rank in the chain, and the rms values are written back IN PLACE at that rank (rank <= frame index, and a
-//   barrier separates a tile's loads from its stores, so nothing is overwritten before it is read).  Four threads
-//   form one 32-frame group and leave its record {mask, rank of its first flagged frame}.
-// Phase 1: speculation and repair over the dense list of n_f steps.  S lanes take S contiguous segments of equal
+// k_compact has turned the chain's rms plane into a dense list of the n_f flagged frames (below threshold the reference
+// never releases - max_attenuation = 0 => dec = 0 - so unflagged frames are no-ops of the recurrence).
+// Speculation and repair over the dense list of n_f steps.  S lanes take S contiguous segments of equal
 //   step count (a multiple of 8).  Pass 1 starts every segment from a guess - the max_attenuation of the step just
 //   before it, which is exactly right whenever the compressor was clamped there; lane 0 from 0, as the reference
 //   resets the attenuation per chunk.  In a repair pass lane t takes the end value lane t-1 produced in the previous
@@ -607,21 +626,80 @@ constexpr int kChainMaxThreads = 256;
 
 struct RmsBlk { uint32_t w[4]; };         // 8 consecutive entries of the dense rms list
 
-// entries [i, i+8) of the list, entries at or past `lim` read as 0 (= the no-op table entry).  Plain loads: the list
-// was written by this kernel.
-__device__ __forceinline__ RmsBlk list_load(const uint16_t *lp, int64_t i, int64_t lim, bool vec) {
+// entries [i, i+8) of the list, entries at or past `lim` read as 0 (= the no-op table entry)
+__device__ __forceinline__ RmsBlk list_load(const uint16_t *__restrict__ lp, int64_t i, int64_t lim, bool vec) {
     RmsBlk q;
     q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0;
     if (vec && i + 8 <= lim) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(lp + i);
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(lp + i));
         q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
     } else if (i < lim) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (i + k < lim) q.w[k >> 1] |= (uint32_t)lp[i + k] << ((k & 1) * 16);
+            if (i + k < lim) q.w[k >> 1] |= (uint32_t)__ldg(lp + i + k) << ((k & 1) * 16);
     }
     return q;
 }
+
+// k_compact: one CTA per k_window_flag tile (2048 frames of one chain).  The tile's rank in its chain is the sum of
+// the flagged counts of the chain's earlier tiles (a few hundred ints, read from L2); inside the tile a CTA-wide
+// exclusive scan gives every flagged frame its rank.  Writes the rms values of the flagged frames to the chain's
+// dense list, the group records, and - from the chain's last tile - the chain's flagged-frame count.
+__global__ void __launch_bounds__(kWfThreads)
+k_compact(const WfJob *__restrict__ jobs, const ChainJob *__restrict__ chains, int chain_lo, const uint16_t *__restrict__ rms,
+          const int *__restrict__ tile_cnt, uint16_t *__restrict__ list, GrpRec *__restrict__ grp, int *__restrict__ n_flagged,
+          int64_t mb_frames) {
+    __shared__ int s_warp[kWfThreads / 32], s_before[kWfThreads / 32];
+    const WfJob job = jobs[blockIdx.x];
+    const ChainJob cj = chains[job.chain];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int tile = (int)blockIdx.x;
+    const int mine = tile_cnt[tile];
+    const bool last = job.tile_begin + kWfTile >= cj.n;
+    // flagged frames of the chain in front of this tile
+    int before = 0;
+    for (int j = cj.tile0 + t; j < tile; j += kWfThreads) before += tile_cnt[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(kFull, before, d);
+    if (lane == 0) s_before[wid] = before;
+    const uint16_t *rp = rms + (int64_t)cj.band * mb_frames + cj.mb_begin;
+    uint16_t *lp = list + (int64_t)cj.band * mb_frames + cj.mb_begin;
+    GrpRec *gr = grp + cj.grp_begin;
+    const int64_t n = cj.n, i = job.tile_begin + (int64_t)t * 8;
+    const bool vec = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
+    const RmsBlk q = list_load(rp, i, n, vec);
+    unsigned m8 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if ((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
+    const int cnt = __popc(m8);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    // the four threads of a 32-frame group sit in one warp (t & 3 == 0 leads)
+    const unsigned m1 = __shfl_down_sync(kFull, m8, 1), m2 = __shfl_down_sync(kFull, m8, 2), m3 = __shfl_down_sync(kFull, m8, 3);
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kWfThreads / 32; ++w) {
+        base += s_before[w];
+        if (w < wid) base += s_warp[w];
+    }
+    const int rank = base + incl - cnt;
+    if ((t & 3) == 0 && i < n) gr[i >> 5] = GrpRec{m8 | (m1 << 8) | (m2 << 16) | (m3 << 24), (uint32_t)rank};
+    if (mine) {
+        int slot = rank;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m8 & (1u << k)) lp[slot++] = (uint16_t)((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+    }
+    if (last && t == kWfThreads - 1) n_flagged[job.chain - chain_lo] = rank + cnt;
+}
+
 
 // table entries of the 8 steps of a block: one 32-byte gather each (entry 0 is all zeros = no-op).  Plain asm, not
 // volatile: the table is constant and tbl + r is always a valid aligned entry, so the compiler may schedule the loads
@@ -634,13 +712,61 @@ __device__ __forceinline__ void list_entries(AttEntry *e, const AttEntry *tbl, c
     }
 }
 
+// What a repair walk learns about the trajectory it stores (the one from the NEW start), so that the next change of
+// the start can usually be applied without walking again:
+//   the first p steps all took the release branch (attenuation parked above max_attenuation: att' = att - dec).
+//   Inside one binade a double is (exponent, integer mantissa n), and fl(n u - dec) = (n - q) u with q = the nearest
+//   integer to dec / u - the SAME q for every n of the binade unless dec / u is exactly half-way (a tie, decided by
+//   the parity of n).  So on that prefix a start moved by d ulps moves every value by d ulps, exactly, as long as
+//   (a) no step is a tie, (b) the moved values stay in the binade, (c) they stay above every max_attenuation
+//   (margin = min over the prefix of bits(att) - bits(M) stays positive).
+//   At step p the stored trajectory left the release branch.  If it was CLAMPED there (tau <= att <= M -> M) and the
+//   moved value still lies in [tau, M], both trajectories are M from step p on: the end value does not move.
+//   If the whole segment is parked (p = its length) the end value moves by d as well.
+// A chain parked for seconds (pydub releases by M / release_frames per frame, hardly at all) therefore costs one
+// walk per segment plus an integer add per stored value, instead of one walk per segment PER PASS.
+struct SegSum {
+    long long margin;      // min over the parked prefix of bits(att before the step) - bits(M of the step)
+    long long at_p;        // bits(att before step p)
+    long long lo, hi;      // bits(tau), bits(M) of step p
+    int64_t p;             // steps in the parked prefix
+    int exp0;              // exponent field of the start
+    bool open;             // still inside the prefix (while walking); afterwards: the whole segment is parked
+    bool ok;               // no tie, one binade
+};
+
+__device__ __forceinline__ void segsum_begin(SegSum &u, double start) {
+    u.margin = 0x7fffffffffffffffLL; u.at_p = 0; u.lo = 0; u.hi = -1; u.p = 0;
+    u.exp0 = (int)(__double_as_longlong(start) >> 52);
+    u.open = true; u.ok = u.exp0 > 0;
+}
+
 // 8 steps of the recurrence (steps [i, i+8) of the list) from attenuation b - with DUAL also from a - storing the
 // b trajectory.  True when DUAL and a == b afterwards.
 template <bool DUAL>
-__device__ __forceinline__ bool list_step8(const AttEntry *e, double *al, int64_t i, int64_t lim, bool avec, double &a, double &b) {
+__device__ __forceinline__ bool list_step8(const AttEntry *e, double *al, int64_t i, int64_t lim, bool avec, double &a, double &b,
+                                           SegSum &u, double &max_m, double &sum_dec) {
     double o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+        if (!DUAL) { max_m = fmax(max_m, e[k].m); sum_dec += e[k].dec; }   // the first walk also sizes the segment (forecast below)
+        if (DUAL && u.open && i + k < lim) {
+            const long long ib = __double_as_longlong(b), im = __double_as_longlong(e[k].m);
+            if (ib > im) {
+                u.margin = min(u.margin, ib - im);
+                const long long id = __double_as_longlong(e[k].dec);
+                if (id != 0) {
+                    const int ed = (int)(id >> 52);
+                    const long long mant = (id & 0xfffffffffffffLL) | (ed ? (1LL << 52) : 0LL);
+                    if ((ed ? ed : 1) + (__ffsll(mant) - 1) == u.exp0 - 1) u.ok = false;      // half an ulp exactly: a tie
+                }
+                ++u.p;
+            } else {
+                u.open = false;
+                u.at_p = ib; u.lo = __double_as_longlong(e[k].tau); u.hi = im;
+                if ((int)(ib >> 52) != u.exp0) u.ok = false;
+            }
+        }
         b = att_update(b, e[k].m, e[k].inc, e[k].dec, e[k].tau);
         if (DUAL) a = att_update(a, e[k].m, e[k].inc, e[k].dec, e[k].tau);
         o[k] = b;
@@ -661,7 +787,7 @@ __device__ __forceinline__ bool list_step8(const AttEntry *e, double *al, int64_
 // first block that leaves the two bit-equal.  b holds the attenuation reached.
 template <bool DUAL>
 __device__ __forceinline__ bool list_walk(const uint16_t *lp, const AttEntry *tbl, double *al, int64_t b0, int64_t b1, bool vec,
-                                          bool avec, double a, double &b) {
+                                          bool avec, double a, double &b, SegSum &u, double &max_m, double &sum_dec) {
     if (b0 >= b1) return false;
     RmsBlk r0 = list_load(lp, b0, b1, vec), r1 = list_load(lp, b0 + 8, b1, vec);
     AttEntry ea[8], eb[8];
@@ -669,72 +795,28 @@ __device__ __forceinline__ bool list_walk(const uint16_t *lp, const AttEntry *tb
     for (int64_t i = b0; i < b1; i += 16) {
         r0 = list_load(lp, i + 16, b1, vec);
         list_entries(eb, tbl, r1);
-        if (list_step8<DUAL>(ea, al, i, b1, avec, a, b)) return true;
+        if (list_step8<DUAL>(ea, al, i, b1, avec, a, b, u, max_m, sum_dec)) return true;
         if (i + 8 >= b1) break;
         r1 = list_load(lp, i + 24, b1, vec);
         list_entries(ea, tbl, r0);
-        if (list_step8<DUAL>(eb, al, i + 8, b1, avec, a, b)) return true;
+        if (list_step8<DUAL>(eb, al, i + 8, b1, avec, a, b, u, max_m, sum_dec)) return true;
     }
     return false;
 }
 
 __global__ void __launch_bounds__(kChainMaxThreads)
-k_att_chain(const ChainJob *__restrict__ jobs, uint16_t *rms, const AttEntry *__restrict__ tables, GrpRec *__restrict__ grp,
-            double *att, int64_t mb_frames, int n_lanes, int *__restrict__ stats) {   // stats[chain] = {flagged steps, passes}
-    __shared__ int s_warp[2][kChainMaxThreads / 32];
-    __shared__ double s_end[kChainMaxThreads];
+k_att_chain(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ list, const int *__restrict__ n_flagged,
+            const AttEntry *__restrict__ tables, double *att, int64_t mb_frames, int n_lanes,
+            int *__restrict__ stats) {   // stats[chain] = {flagged steps, passes}
+    __shared__ double s_end[kChainMaxThreads], s_maxm[kChainMaxThreads], s_dec[kChainMaxThreads], s_guess[kChainMaxThreads];
     const ChainJob job = jobs[blockIdx.x];
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, n_warps = (blockDim.x + 31) >> 5;
-    uint16_t *lp = rms + (int64_t)job.band * mb_frames + job.mb_begin;
+    const int t = threadIdx.x;
+    const uint16_t *lp = list + (int64_t)job.band * mb_frames + job.mb_begin;
     double *al = att + (int64_t)job.band * mb_frames + job.mb_begin;
-    GrpRec *gr = grp + job.grp_begin;
     const AttEntry *tbl = tables + (size_t)job.table * 32769;
-    const int64_t n = job.n;
     const bool vec = (reinterpret_cast<uintptr_t>(lp) & 15) == 0;
     const bool avec = (reinterpret_cast<uintptr_t>(al) & 15) == 0;
-
-    // ---- phase 0: compact the flagged frames of the rms plane in place, leave the group records -----------------
-    int64_t running = 0;
-    const int64_t tile = (int64_t)blockDim.x * 8;
-    int par = 0;
-    RmsBlk qn = list_load(lp, (int64_t)t * 8, n, vec);
-    for (int64_t t0 = 0; t0 < n; t0 += tile, par ^= 1) {
-        const int64_t i = t0 + (int64_t)t * 8;
-        const RmsBlk q = qn;
-        qn = list_load(lp, i + tile, n, vec);     // next tile's words in flight (they lie above every store of this tile)
-        unsigned m8 = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if ((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
-        const int cnt = __popc(m8);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += v;
-        }
-        if (lane == 31) s_warp[par][wid] = incl;
-        // the four threads of a 32-frame group sit in one warp (t & 3 == 0 leads)
-        const unsigned m1 = __shfl_down_sync(kFull, m8, 1), m2 = __shfl_down_sync(kFull, m8, 2), m3 = __shfl_down_sync(kFull, m8, 3);
-        __syncthreads();          // every load of this tile has been consumed; s_warp[par] is complete
-        int before = 0, total = 0;
-        for (int w = 0; w < n_warps; ++w) {
-            const int c = s_warp[par][w];
-            if (w < wid) before += c;
-            total += c;
-        }
-        const int64_t rank = running + before + incl - cnt;
-        if ((t & 3) == 0 && i < n) gr[i >> 5] = GrpRec{m8 | (m1 << 8) | (m2 << 16) | (m3 << 24), (uint32_t)rank};
-        int64_t slot = rank;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (m8 & (1u << k)) lp[slot++] = (uint16_t)((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-        running += total;
-        // no second barrier: the next tile uses the other half of s_warp, reads frames >= t0 + tile, and every store of
-        // this tile lands below t0 + tile
-    }
-    const int64_t n_f = running;
-    __syncthreads();              // the dense list is complete and visible to the CTA
+    const int64_t n_f = n_flagged[blockIdx.x];        // k_compact counted the chain's flagged frames
 
     // ---- phase 1: the recurrence over n_f steps in S segments, speculation and repair ---------------------------
     int S = n_lanes < 1 ? 1 : (n_lanes > (int)blockDim.x ? (int)blockDim.x : n_lanes);
@@ -743,24 +825,74 @@ k_att_chain(const ChainJob *__restrict__ jobs, uint16_t *rms, const AttEntry *__
     const int S_used = (int)((n_f + seg - 1) / seg);
     const int64_t b0 = min(n_f, (int64_t)t * seg), b1 = min(n_f, b0 + seg);
     double start = 0.0;
-    if (t > 0 && b0 < b1) start = tbl[lp[b0 - 1]].m;
+    if (t > 0 && b0 < b1) start = tbl[__ldg(lp + b0 - 1)].m;
     double end = start;
-    list_walk<false>(lp, tbl, al, b0, b1, vec, avec, 0.0, end);
+    SegSum u;
+    segsum_begin(u, start);
+    u.ok = false;                                             // nothing is known after the plain first walk
+    double max_m = 0.0, sum_dec = 0.0;
+    list_walk<false>(lp, tbl, al, b0, b1, vec, avec, 0.0, end, u, max_m, sum_dec);
+    // Forecast (decides only which guesses are tried next, never what is stored).  Follow the attenuation from lane 0's
+    // end - which is final - through the segments: where it enters a segment above everything that segment can ask for,
+    // even after all the release it could get there, the true trajectory is parked throughout.  Such a lane walks
+    // again from the forecast value: a start in the right binade and within a few thousand ulps of the true one, so
+    // that when the true start arrives (one lane per pass) it is applied as an integer shift (SegSum) instead of
+    // another walk - a chain parked for its whole length costs two walks per lane instead of one walk per lane per pass.
+    s_end[t] = end; s_maxm[t] = max_m; s_dec[t] = sum_dec; s_guess[t] = -1.0;
+    __syncthreads();
+    if (t == 0) {
+        double lb = s_end[0];
+        for (int v = 1; v < S_used; ++v) {
+            const double lo = lb - 1.000001 * s_dec[v];
+            if (lb > 0.0 && lo > s_maxm[v]) { s_guess[v] = lb; lb = lo; }
+            else lb = s_end[v];
+        }
+    }
+    __syncthreads();
+    long long pending = 0;                                    // ulps still to be added to the stored prefix [b0, b0 + u.p)
+    auto flush = [&]() {
+        if (pending) {
+            for (int64_t i = b0; i < b0 + u.p; ++i) al[i] = __longlong_as_double(__double_as_longlong(al[i]) + pending);
+            pending = 0;
+        }
+    };
     int passes = 1;
     for (;;) {
         s_end[t] = end;
         __syncthreads();
-        const double from = (t > 0 && t < S_used) ? s_end[t - 1] : 0.0;
+        double from = (t > 0 && t < S_used) ? s_end[t - 1] : 0.0;
+        if (passes == 1 && t < S_used && s_guess[t] >= 0.0) from = s_guess[t];
         const bool redo = t < S_used && __double_as_longlong(from) != __double_as_longlong(start);
         const int n_redo = __syncthreads_count(redo);     // also orders the reads of s_end before the next round's writes
         if (!n_redo) break;
         ++passes;
         if (redo) {
-            double b = from;
-            if (!list_walk<true>(lp, tbl, al, b0, b1, vec, avec, start, b)) end = b;
-            start = from;
+            const long long fb = __double_as_longlong(from), d = fb - __double_as_longlong(start);
+            const bool parked = u.open;                   // the whole segment is a parked prefix
+            bool quick = u.ok && (int)(fb >> 52) == u.exp0 && (d >= 0 || u.p == 0 || u.margin > -d);
+            if (quick && parked) quick = (int)((__double_as_longlong(end) + d) >> 52) == u.exp0;
+            // step p must clamp (tau <= att <= M -> M) on the stored trajectory and on the moved one
+            if (quick && !parked) quick = u.at_p >= u.lo && u.at_p <= u.hi && u.at_p + d >= u.lo && u.at_p + d <= u.hi &&
+                                          (int)((u.at_p + d) >> 52) == u.exp0;
+            if (quick) {                                  // every stored value of the prefix moves by d ulps, nothing else does
+                pending += d;
+                if (u.p) u.margin += d;
+                if (parked) end = __longlong_as_double(__double_as_longlong(end) + d);
+                else u.at_p += d;
+                start = from;
+            } else {
+                flush();                                  // the stored values must be the trajectory from `start` again
+                double b = from;
+                segsum_begin(u, from);
+                const bool met = list_walk<true>(lp, tbl, al, b0, b1, vec, avec, start, b, u, max_m, sum_dec);
+                if (!met) end = b;
+                // still "open" means every step walked was parked: that describes the segment only if the walk covered it
+                if (u.open && (met || (int)(__double_as_longlong(end) >> 52) != u.exp0)) u.ok = false;
+                start = from;
+            }
         }
     }
+    flush();
     if (stats && t == 0) { stats[2 * blockIdx.x] = (int)min(n_f, (int64_t)0x7fffffff); stats[2 * blockIdx.x + 1] = passes; }
 }
 
@@ -851,8 +983,12 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_l
 // whole track (the reference measures the concatenated file), so warm-up may cross chunk joins.
 // One thread per tile of sub-blocks, both channels (two independent chains).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+struct KwCfg { double b0, b1, b2, a1, a2, ra1, ra2; };   // pre-filter biquad; RLB denominators (numerator 1 -2 1)
+
+// UNI: every track of the launch has the same K filter (same sample rate): coefficients from the kernel parameter.
+template <bool UNI>
+__global__ void __launch_bounds__(128, 5)
+k_kweight_energy(const __grid_constant__ KwCfg kc, const KwJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
                  const TrackDev *__restrict__ tdev, const int16_t *__restrict__ pre,
                  double *__restrict__ energy, int *__restrict__ peak) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -860,7 +996,8 @@ k_kweight_energy(const KwJob *__restrict__ jobs, int n_jobs, const ame_track_par
     const KwJob job = jobs[j];
     const ame_track_params *tp = tracks + job.track;
     const TrackDev td = tdev[job.track];
-    const ame_biquad k0 = tp->kw[0], k1 = tp->kw[1];
+    const ame_biquad k0 = UNI ? ame_biquad{kc.b0, kc.b1, kc.b2, kc.a1, kc.a2} : tp->kw[0];
+    const ame_biquad k1 = UNI ? ame_biquad{1.0, -2.0, 1.0, kc.ra1, kc.ra2} : tp->kw[1];
     const int64_t s100 = td.s100;
     const int64_t base = tp->offset_frames;                      // multiple of 8
     const int64_t t_begin = (int64_t)job.sb_begin * s100;        // relative to the track

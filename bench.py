@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--e2e-waves", type=int, default=32)
     ap.add_argument("--chain-warps", type=int, default=0, help="ame_plan_options.chain_warps (0 = auto, -1 = queue kernel)")
     ap.add_argument("--waves", type=int, default=6, help="plan waves of the device-resident path")
+    ap.add_argument("--slots", type=int, default=0, help="workspace slots (0 = min(waves, 4))")
+    ap.add_argument("--fuse-kw", action="store_true", help="K-weighting in the k_eq epilogue for tracks without multiband (A/B)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -197,7 +199,8 @@ def run_b200(args, rank, world, local_rank):
     ids = nb[:2] + mb + nb[2:]
     settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
     plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves, chain_warps=args.chain_warps,
-                      kw_tile_subblocks=args.kw_tile, eq_tile_frames=args.eq_tile, xover_tile_frames=args.xover_tile)
+                      kw_tile_subblocks=args.kw_tile, eq_tile_frames=args.eq_tile, xover_tile_frames=args.xover_tile,
+                      n_slots=args.slots, fuse_kw=args.fuse_kw)
     assert plan.total_frames == n_tr * ((n + 7) // 8 * 8)
     tracks = synth.torch_track_batch(n_tr, secs, fs, dev, first_track_id=first)        # [n_tr, n, 2] int16
     d_in = torch.zeros((plan.total_frames, 2), dtype=torch.int16, device=dev)
@@ -314,7 +317,7 @@ def run_b200(args, rank, world, local_rank):
                            "parallelism": f"by-track x{world}, no collective", "plan_waves": args.waves,
                            "l2": f"inputs larger than L2 ({d_in.numel() * 2 / 1e9:.2f} GB per GPU per pass)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "workspace_gb": round(plan.workspace_bytes / 1e9, 2)}
+                "workspace_gb": round(plan.workspace_bytes / 1e9, 2), "chain_stats": plan.chain_stats()}
         print(json.dumps(line), flush=True)
     plan.close()
     if world > 1:
