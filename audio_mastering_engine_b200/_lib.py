@@ -47,7 +47,7 @@ class TrackResult(C.Structure):
 class PlanOptions(C.Structure):
     _fields_ = [("eq_tile_frames", C.c_int32), ("xover_tile_frames", C.c_int32), ("kw_tile_subblocks", C.c_int32),
                 ("host_io", C.c_int32), ("n_waves", C.c_int32), ("chain_warps", C.c_int32), ("n_slots", C.c_int32),
-                ("fuse_kw", C.c_int32), ("precision", C.c_int32)]
+                ("precision", C.c_int32)]
 
 
 class AmeError(RuntimeError):

@@ -133,8 +133,6 @@ struct Wave {
     bool xover_uni = false, kw_uni = false;        // all multiband tracks share the crossover / all k_kweight_energy tracks the K filter
     XoverCfg xover{};
     KwCfg kw{};
-    struct EqLaunch { int job_lo, job_n, table; bool plain, fused; };   // which of k_eq / k_eq_kw have work in it
-    std::vector<EqLaunch> eq_launches;             // k_eq launches of the wave: one per table of <= kMaxEqCfg configurations
 };
 
 // Per-wave workspace.  A plan has n_slots of them; wave w runs in slot w % n_slots on that slot's stream, so a slot is
@@ -166,8 +164,6 @@ struct ame_plan {
     int64_t slot_frames = 0, slot_groups = 0;
     int slot_tiles = 0, slot_chains = 0;
     int64_t n_sb_total = 0;
-    std::vector<char> fuse_kw;            // per track: K-weighting runs in the k_eq epilogue
-    std::vector<EqCfgTable> eq_tables;    // per k_eq launch: the coefficient sets of its tracks (passed as the kernel parameter)
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
     int n_sm = 148, chain_warps = 0;      // see chain_threads()
     size_t ws_bytes = 0;
@@ -232,16 +228,6 @@ int dmalloc(ame_plan *p, void **ptr, size_t bytes) {
 }
 
 // split chunk [cb, ce) into ceil(n / T) near-equal tiles whose interior boundaries are multiples of 8
-// the same with every interior boundary at cb + j * t, t a multiple of `q` frames (tracks whose K-weighting runs in
-// the k_eq epilogue: tiles start on the 100 ms sub-block grid, on which their chunks start too)
-void tile_jobs_grid(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T, int64_t q) {
-    const int64_t n = ce - cb;
-    if (n <= 0) return;
-    const int64_t k = (n + T - 1) / T;
-    const int64_t t = align_up((n + k - 1) / k, q);
-    for (int64_t b = cb; b < ce; b += t) out.push_back(TileJob{cb, b, std::min(b + t, ce), track, variant});
-}
-
 void tile_jobs(std::vector<TileJob> &out, int track, int variant, int64_t cb, int64_t ce, int64_t T) {
     const int64_t n = ce - cb;
     if (n <= 0) return;
@@ -288,67 +274,37 @@ double eq_cost_per_frame(const ame_track_params &t) {
     if (t.eq[3].kind != AME_EQ_BYPASS) c += 16.0;
     return c;
 }
-constexpr double kEqCostKw = 30.0;                      // K-weighting epilogue: two sections + squares, two channels
 
 // k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
-// both variants one after the other: every track gets a whole number of warps.  A thread's time is about
-// (tile + warm-up) * cost per frame, and both the cost (no EQ at all ... 4 stages + warmth + K-weighting) and the
-// warm-up (0 ... EQ + K filter) differ a lot between tracks: give every track the tile length that makes that
-// product equal to one common budget, the smallest budget whose job count fits `slots` threads.
-struct EqTrack { double cost; int64_t warm, min_tile, q; };
-
-int64_t eq_jobs_of_track(const std::vector<int64_t> &chunks, int64_t T) {
-    int64_t jobs = 0;
-    for (int64_t cn : chunks) jobs += (cn + T - 1) / T;
-    return (jobs + 31) / 32 * 32;
-}
-
-std::vector<int64_t> eq_tiles_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<EqTrack> &et,
-                                        int t_lo, int t_hi, int64_t slots) {
-    auto tile_of = [&](int t, double budget) {
-        const EqTrack &e = et[t];
-        int64_t T = (int64_t)(budget / e.cost) - e.warm;
-        T = T / e.q * e.q;
-        return std::max(T, e.min_tile);
-    };
-    auto total = [&](double budget) {
-        int64_t jobs = 0;
-        for (int t = t_lo; t < t_hi; ++t) jobs += eq_jobs_of_track(chunks[t], tile_of(t, budget));
-        return jobs;
-    };
-    double lo = 0.0, hi = 1.0;
+// both variants one after the other.  Every track therefore gets a whole number of warps, in proportion to its
+// cost (frames x cost per frame), and its 32 * warps jobs are spread over its chunks by length.
+std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<double> &cost,
+                                    int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
+    const int n = (int)chunks.size();
+    std::vector<int> warps(n, 0);
+    std::vector<double> weight(n, 0.0);
+    std::vector<int> cap(n, 0);
+    double wsum = 0;
     for (int t = t_lo; t < t_hi; ++t) {
-        int64_t longest = 1;
-        for (int64_t cn : chunks[t]) longest = std::max(longest, cn);
-        hi = std::max(hi, (double)(longest + et[t].warm + et[t].q) * et[t].cost);
+        int64_t frames = 0, max_jobs = 0;
+        for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tile); }
+        weight[t] = (double)frames * cost[t];
+        cap[t] = (int)std::max<int64_t>(1, (max_jobs + 31) / 32);
+        wsum += weight[t];
     }
-    if (total(lo) > slots)
-        for (int it = 0; it < 60; ++it) {        // total() is non-increasing in the budget
-            const double mid = 0.5 * (lo + hi);
-            if (total(mid) <= slots) hi = mid; else lo = mid;
-        }
-    else hi = lo;
-    std::vector<int64_t> T(chunks.size(), 0);
-    for (int t = t_lo; t < t_hi; ++t) T[t] = tile_of(t, hi);
-    return T;
-}
-
-EqCfg eq_cfg_of(const ame_track_params &t) {
-    EqCfg c;
-    std::memset(&c, 0, sizeof c);
-    c.wl_b0 = t.wl_b0; c.wl_b1 = t.wl_b1; c.wl_a1 = t.wl_a1; c.wl_gm1 = t.wl_gm1;
-    c.wh_b0 = t.wh_b0; c.wh_b1 = t.wh_b1; c.wh_a1 = t.wh_a1; c.wh_gm1 = t.wh_gm1;
-    c.s0_b0 = t.eq[0].s[0].b0; c.s0_a1 = t.eq[0].s[0].a1; c.s0_a2 = t.eq[0].s[0].a2; c.g0 = t.eq[0].g; c.gm0 = t.eq[0].gm1;
-    c.p1_b0 = t.eq[1].s[0].b0; c.gm1 = t.eq[1].gm1;
-    c.p2_b0 = t.eq[2].s[0].b0; c.gm2 = t.eq[2].gm1;
-    for (int i = 0; i < 4; ++i) {
-        c.p1_a1[i] = t.eq[1].s[i].a1; c.p1_a2[i] = t.eq[1].s[i].a2;
-        c.p2_a1[i] = t.eq[2].s[i].a1; c.p2_a2[i] = t.eq[2].s[i].a2;
+    int64_t avail = std::max<int64_t>(t_hi - t_lo, slots / 32);
+    std::vector<std::pair<double, int>> rem;
+    int64_t used = 0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        const double share = wsum > 0 ? avail * weight[t] / wsum : 1.0;
+        warps[t] = std::min(cap[t], std::max(1, (int)share));
+        used += warps[t];
+        rem.emplace_back(share - warps[t], t);
     }
-    c.s3_b0 = t.eq[3].s[0].b0; c.s3_a1 = t.eq[3].s[0].a1; c.s3_a2 = t.eq[3].s[0].a2; c.g3 = t.eq[3].g; c.gm3 = t.eq[3].gm1;
-    c.k0b0 = t.kw[0].b0; c.k0b1 = t.kw[0].b1; c.k0b2 = t.kw[0].b2; c.k0a1 = t.kw[0].a1; c.k0a2 = t.kw[0].a2;
-    c.k1a1 = t.kw[1].a1; c.k1a2 = t.kw[1].a2;
-    return c;
+    std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+    for (size_t i = 0; i < rem.size() && used < avail; ++i)
+        if (warps[rem[i].second] < cap[rem[i].second]) { ++warps[rem[i].second]; ++used; }
+    return warps;
 }
 
 int validate(const ame_track_params &t, int idx) {
@@ -456,22 +412,10 @@ Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) 
 }
 
 int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cudaStream_t s) {
-    const int nt = w.track_hi - w.track_lo;
-    if (nt > 0) CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));   // k_eq's K-weighting epilogue feeds it
     if (!w.eq_n) return AME_OK;
     t_begin(p, S_EQ, s);
-    for (const Wave::EqLaunch &g : w.eq_launches) {
-        if (g.plain) {
-            k_eq<<<(g.job_n + 127) / 128, 128, 0, s>>>(p->eq_tables[g.table], p->d_eq_jobs + g.job_lo, g.job_n, p->d_tracks, p->d_tdev,
-                                                       p->d_luts, d_in, d_pre, p->d_energy, p->d_peak);
-            LAUNCH_CHECK(p);
-        }
-        if (g.fused) {
-            k_eq_kw<<<(g.job_n + 127) / 128, 128, 0, s>>>(p->eq_tables[g.table], p->d_eq_jobs + g.job_lo, g.job_n, p->d_tracks,
-                                                          p->d_tdev, p->d_luts, d_in, d_pre, p->d_energy, p->d_peak);
-            LAUNCH_CHECK(p);
-        }
-    }
+    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+    LAUNCH_CHECK(p);
     t_end(p, S_EQ, s);
     return AME_OK;
 }
@@ -525,6 +469,7 @@ int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
 int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, cudaStream_t s) {
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
+    CU(cudaMemsetAsync(p->d_peak + w.track_lo, 0, (size_t)nt * 4, s));
     if (w.kw_n) {
         t_begin(p, S_KW, s);
         if (w.kw_uni)
@@ -649,7 +594,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     std::vector<std::pair<int64_t, int64_t>> spans;
     p->mb_offset.assign(n_tracks, -1);
     p->tdev.resize(n_tracks);
-    p->fuse_kw.assign(n_tracks, 0);
     int64_t sum_frames = 0;
     for (int t = 0; t < n_tracks; ++t) {
         ame_track_params &tp = p->tracks[t];
@@ -668,15 +612,6 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         p->tdev[t].first_block = tp.halo_frames ? std::max<int>(0, (int)(tp.halo_frames / s100) - 3) : 0;
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
-        // K-weighting in the k_eq epilogue: the k_eq output must BE the pre-normalisation signal (no multiband stage,
-        // no halo of another shard in front), tiles and chunks must lie on the 100 ms grid, and the RLB numerator must
-        // be the 1 -2 1 the kernel hard-wires
-        const int64_t cf = tp.chunk_frames;
-        const bool one_chunk = cf <= 0 || tp.n_frames <= cf;
-        p->fuse_kw[t] = o.fuse_kw > 0 && !(tp.flags & AME_F_MULTIBAND) && tp.halo_frames == 0 && s100 >= 8 &&
-                        (one_chunk || cf % s100 == 0) && tp.kw[1].b0 == 1.0 && tp.kw[1].b1 == -2.0 && tp.kw[1].b2 == 1.0;
-        p->tdev[t].fused = p->fuse_kw[t];
-        p->tdev[t].eq_cfg = 0;
         p->tdev[t].pad = 0;
     }
     for (size_t i = 1; i < spans.size(); ++i)
@@ -752,32 +687,22 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     const int64_t split_slots = (int64_t)n_sm * std::max(occ_split, 1) * 128 / share;
     constexpr int64_t kMinTile = 512;
     int64_t split_tile = kMinTile;
-    std::vector<EqTrack> eq_track(n_tracks);
-    std::vector<int64_t> eq_tile_of(n_tracks, kMinTile);
+    std::vector<double> eq_cost(n_tracks);
+    std::vector<int> eq_warps(n_tracks, 1);
     int max_warm_kw = 0, min_s100 = 1 << 30;
-    int64_t n_sb_kw = 0;                                  // sub-blocks left to k_kweight_energy
     for (int t = 0; t < n_tracks; ++t) {
-        const ame_track_params &tp = p->tracks[t];
-        bool any_eq = false;
-        for (int s = 0; s < 4; ++s) any_eq = any_eq || tp.eq[s].kind != AME_EQ_BYPASS;
-        EqTrack &e = eq_track[t];
-        e.cost = eq_cost_per_frame(tp) + (p->fuse_kw[t] ? kEqCostKw : 0.0);
-        e.warm = (any_eq ? tp.warm_eq : 0) + (p->fuse_kw[t] ? tp.warm_kw : 0);
-        e.q = p->fuse_kw[t] ? p->tdev[t].s100 : 8;
-        e.min_tile = p->fuse_kw[t] ? p->tdev[t].s100 : kMinTile;
-        if (!p->fuse_kw[t]) {
-            n_sb_kw += p->tdev[t].n_sb;
-            max_warm_kw = std::max(max_warm_kw, p->tracks[t].warm_kw);
-            min_s100 = std::min(min_s100, p->tdev[t].s100);
-        }
+        eq_cost[t] = eq_cost_per_frame(p->tracks[t]);
+        max_warm_kw = std::max(max_warm_kw, p->tracks[t].warm_kw);
+        min_s100 = std::min(min_s100, p->tdev[t].s100);
     }
+    const int64_t n_sb_kw = p->n_sb_total;
     for (const Wave &wv : p->waves) {
         std::vector<int64_t> cm;
         for (int t = wv.track_lo; t < wv.track_hi; ++t)
             if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
         split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
-        const std::vector<int64_t> tt = eq_tiles_per_track(chunks_all, eq_track, wv.track_lo, wv.track_hi, eq_slots);
-        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_tile_of[t] = tt[t];
+        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, kMinTile);
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
     }
     p->eq_tile = 0;
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
@@ -810,38 +735,12 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chunk_lo = (int)mb_chunks.size(); wv.kw_lo = (int)kw_jobs.size(); wv.gain_lo = (int)gain_jobs.size();
         wv.seg_lo = n_seg_total;
         int64_t n_groups = 0;                          // group records of this wave (slot-local indices)
-        std::map<std::string, int> cfg_index;          // coefficient sets of the current k_eq launch
-        p->eq_tables.emplace_back();
-        std::memset(&p->eq_tables.back(), 0, sizeof(EqCfgTable));
-        wv.eq_launches.push_back(Wave::EqLaunch{(int)eq_jobs.size(), 0, (int)p->eq_tables.size() - 1, false, false});
         for (int t = wv.track_lo; t < wv.track_hi; ++t) {
             ame_track_params &tp = p->tracks[t];
-            {
-                const EqCfg cfg = eq_cfg_of(tp);
-                const std::string key((const char *)&cfg, sizeof cfg);
-                auto it = cfg_index.find(key);
-                if (it == cfg_index.end()) {
-                    if ((int)cfg_index.size() == kMaxEqCfg) {          // table full: this track starts the next launch
-                        wv.eq_launches.back().job_n = (int)eq_jobs.size() - wv.eq_launches.back().job_lo;
-                        cfg_index.clear();
-                        p->eq_tables.emplace_back();
-                        std::memset(&p->eq_tables.back(), 0, sizeof(EqCfgTable));
-                        wv.eq_launches.push_back(Wave::EqLaunch{(int)eq_jobs.size(), 0, (int)p->eq_tables.size() - 1, false, false});
-                    }
-                    const int idx = (int)cfg_index.size();
-                    cfg_index[key] = idx;
-                    p->eq_tables.back().c[idx] = cfg;
-                    p->tdev[t].eq_cfg = idx;
-                } else {
-                    p->tdev[t].eq_cfg = it->second;
-                }
-                (p->fuse_kw[t] ? wv.eq_launches.back().fused : wv.eq_launches.back().plain) = true;
-            }
             int variant = 0;
             for (int s = 0; s < 4; ++s)
                 if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
             if (tp.flags & AME_F_WARMTH) variant |= 16;
-            if (p->fuse_kw[t]) variant |= 32;
             const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
             if (mb) {
                 mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
@@ -864,19 +763,23 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             const size_t eq_first = eq_jobs.size();
             {
                 int64_t c0e = 0;
-                const int64_t q = eq_track[t].q;
+                const int64_t want = (int64_t)eq_warps[t] * 32;
                 for (int64_t cn : chunks_all[t]) {
                     const int64_t cb = tp.offset_frames + tp.halo_frames + c0e, ce = cb + cn;
-                    const int64_t T = o.eq_tile_frames > 0 ? align_up(o.eq_tile_frames, q) : eq_tile_of[t];
-                    if (p->fuse_kw[t]) tile_jobs_grid(eq_jobs, t, variant, cb, ce, T, q);
-                    else tile_jobs(eq_jobs, t, variant, cb, ce, T);
+                    int64_t T;
+                    if (o.eq_tile_frames > 0) {
+                        T = align_up(o.eq_tile_frames, 8);
+                    } else {
+                        const int64_t jc = std::max<int64_t>(1, want * cn / std::max<int64_t>(tp.n_frames, 1));   // floor: never over `want`
+                        T = std::max<int64_t>(kMinTile, align_up((cn + jc - 1) / jc, 8));
+                    }
+                    tile_jobs(eq_jobs, t, variant, cb, ce, T);
                     p->eq_tile = std::max<int>(p->eq_tile, (int)std::min<int64_t>(T, INT32_MAX));
                     c0e += cn;
                 }
                 if (eq_jobs.size() > eq_first) {            // whole warps per track: pad with empty jobs
                     TileJob d = eq_jobs.back();
                     d.tile_begin = d.tile_end;
-                    d.variant &= ~32;                       // an empty job has nothing to measure
                     while ((eq_jobs.size() - eq_first) % 32) eq_jobs.push_back(d);
                 }
             }
@@ -898,14 +801,12 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                 }
                 c0 += cn;
             }
-            if (!p->fuse_kw[t])
-                for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
-                    kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
+            for (int sb = 0; sb < p->tdev[t].n_sb; sb += p->kw_tile_sb)
+                kw_jobs.push_back(KwJob{t, sb, std::min(sb + p->kw_tile_sb, p->tdev[t].n_sb), 0});
             for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
                 gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
                                             tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
         }
-        wv.eq_launches.back().job_n = (int)eq_jobs.size() - wv.eq_launches.back().job_lo;
         {
             bool have_x = false, have_k = false;
             wv.xover_uni = wv.kw_uni = true;
@@ -917,7 +818,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                     if (!have_x) { wv.xover = x; have_x = true; }
                     else if (std::memcmp(&x, &wv.xover, sizeof x)) wv.xover_uni = false;
                 }
-                if (!p->fuse_kw[t]) {
+                {
                     const KwCfg k{tp.kw[0].b0, tp.kw[0].b1, tp.kw[0].b2, tp.kw[0].a1, tp.kw[0].a2, tp.kw[1].a1, tp.kw[1].a2};
                     const bool rlb = tp.kw[1].b0 == 1.0 && tp.kw[1].b1 == -2.0 && tp.kw[1].b2 == 1.0;
                     if (!have_k) { wv.kw = k; have_k = true; }

@@ -52,25 +52,9 @@ struct TrackDev {          // device-side per-track bookkeeping
     int32_t n_sb;          // number of complete 100 ms sub-blocks (halo included)
     int32_t s100;          // frames per 100 ms = (fs + 5) / 10   (ebur128.c)
     int32_t first_block;   // time shards: 400 ms blocks before this one belong to the previous shard / the warm-up
-    int32_t fused;         // K-weighting runs in the k_eq epilogue (no k_kweight_energy jobs)
-    int32_t eq_cfg;        // index of the track's EqCfg in the table of its k_eq launch
     int32_t pad;
     int64_t n_total;       // halo + span frames
 };
-
-// Everything k_eq needs that is the same for every tile of a track.  The table of the configurations of one launch is
-// a KERNEL PARAMETER (constant bank) and the warp's index into it is warp-uniform, so the compiler keeps the
-// coefficients in uniform registers (DFMA takes a UR operand) instead of ~90 of the 255 vector registers a thread has.
-struct EqCfg {
-    double wl_b0, wl_b1, wl_a1, wl_gm1, wh_b0, wh_b1, wh_a1, wh_gm1;      // warmth (:258-266)
-    double s0_b0, s0_a1, s0_a2, g0, gm0;                                  // low shelf 250 Hz
-    double p1_b0, p1_a1[4], p1_a2[4], gm1;                                // peak 1 kHz (4 sections, unit gain but the first)
-    double p2_b0, p2_a1[4], p2_a2[4], gm2;                                // peak 4 kHz
-    double s3_b0, s3_a1, s3_a2, g3, gm3;                                  // high shelf 8 kHz
-    double k0b0, k0b1, k0b2, k0a1, k0a2, k1a1, k1a2;                      // K-weighting (pre-filter; RLB denominators)
-};
-constexpr int kMaxEqCfg = 88;                                            // 88 * 360 B + the other parameters < 32764 B
-struct EqCfgTable { EqCfg c[kMaxEqCfg]; };
 
 __constant__ double c_hist_bounds[1001];
 __constant__ double c_hist_energy[1000];
@@ -83,13 +67,6 @@ __device__ __forceinline__ double bq_step(const ame_biquad &c, double &z0, doubl
     double y = fma(c.b0, x, z0);
     z0 = fma(-c.a1, y, fma(c.b1, x, z1));
     z1 = fma(-c.a2, y, c.b2 * x);
-    return y;
-}
-
-__device__ __forceinline__ double kw_pre(double b0, double b1, double b2, double a1, double a2, double &z0, double &z1, double x) {
-    const double y = fma(b0, x, z0);                       // == bq_step on the same coefficients
-    z0 = fma(-a1, y, fma(b1, x, z1));
-    z1 = fma(-a2, y, b2 * x);
     return y;
 }
 
@@ -141,12 +118,17 @@ __device__ __forceinline__ double shelf_cut(double v, double f, double g) {
     return __dadd_rn(t, __dsub_rn(f, t));
 }
 
-// butter(4, bandpass, sos): numerator signs (+,+,-,-), sections 1..3 of unit gain
-__device__ __forceinline__ double peak_step(double b0, const double *a1, const double *a2, double *z, double x) {
-    double t = bw_step<1>(b0, a1[0], a2[0], z[0], z[1], x);
-    t = bw_step1<1>(a1[1], a2[1], z[2], z[3], t);
-    t = bw_step1<-1>(a1[2], a2[2], z[4], z[5], t);
-    return bw_step1<-1>(a1[3], a2[3], z[6], z[7], t);
+struct PeakCoef { double b0, a1[4], a2[4]; };     // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
+__device__ __forceinline__ void load_peak(PeakCoef &c, const ame_eq_stage &st) {
+    c.b0 = st.s[0].b0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.a1[i] = st.s[i].a1; c.a2[i] = st.s[i].a2; }
+}
+__device__ __forceinline__ double peak_step(const PeakCoef &c, double *z, double x) {
+    double t = bw_step<1>(c.b0, c.a1[0], c.a2[0], z[0], z[1], x);
+    t = bw_step1<1>(c.a1[1], c.a2[1], z[2], z[3], t);
+    t = bw_step1<-1>(c.a1[2], c.a2[2], z[4], z[5], t);
+    return bw_step1<-1>(c.a1[3], c.a2[3], z[6], z[7], t);
 }
 
 // exact int16 -> x / 32768 as double in ONE add: bits of 2^37 + (x + 2^31) * 2^-15, minus 2^37 + 2^16
@@ -156,92 +138,77 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 
 // ------------------------------------------------------------------------------------------------
 // k_eq: int16 in -> [warmth -> int16] -> float32 -> 4-stage EQ in FP64 -> float32 -> [width] -> int16
-//       [-> K-weighting -> 100 ms energies + sample peak, for tracks without a multiband stage]
 // ONE THREAD per tile, both channels: the L and R cascades are two independent dependency chains in one
 // instruction stream (the kernel is bound by FP64 latency, not by registers), and the cross-channel
 // stages (warmth, width, packing) need no shuffles.  MASK = active EQ stages, WARM = warmth on.
-// KW = the K-weighting of the loudness measurement runs in the epilogue on the int16 value just produced (it IS the
-// pre-normalisation signal when the track has no multiband stage), so that signal is not read again: tiles then lie
-// on the track's 100 ms sub-block grid, the warm-up grows by the K filter's, and since the K filter runs through the
-// whole track while the EQ restarts with every chunk, the EQ state is reset when the walk crosses a chunk start.
 // ------------------------------------------------------------------------------------------------
-template <int MASK, bool WARM, bool KW>
-__device__ __forceinline__ void eq_tile(const TileJob &job, const EqCfg &c, const ame_track_params *__restrict__ tp,
-                                        const TrackDev *__restrict__ tdp, const double *__restrict__ luts,
-                                        const int16_t *__restrict__ in, int16_t *__restrict__ pre,
-                                        double *__restrict__ energy, int *__restrict__ peak) {
+template <int MASK, bool WARM>
+__device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
+                                        const double *__restrict__ luts, const int16_t *__restrict__ in,
+                                        int16_t *__restrict__ pre) {
     const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
     const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
-    const bool boost0 = (MASK & 1) && tp->eq[0].kind == AME_EQ_SHELF_BOOST;
-    const bool boost3 = (MASK & 8) && tp->eq[3].kind == AME_EQ_SHELF_BOOST;
+    double wl_b0 = 0, wl_b1 = 0, wl_a1 = 0, wl_gm1 = 0, wh_b0 = 0, wh_b1 = 0, wh_a1 = 0, wh_gm1 = 0;
+    if (WARM) {
+        wl_b0 = tp->wl_b0; wl_b1 = tp->wl_b1; wl_a1 = tp->wl_a1; wl_gm1 = tp->wl_gm1;
+        wh_b0 = tp->wh_b0; wh_b1 = tp->wh_b1; wh_a1 = tp->wh_a1; wh_gm1 = tp->wh_gm1;
+    }
+    double s0_b0 = 0, s0_a1 = 0, s0_a2 = 0, g0 = 0, gm0 = 0, s3_b0 = 0, s3_a1 = 0, s3_a2 = 0, g3 = 0, gm3 = 0, gm1 = 0, gm2 = 0;
+    bool boost0 = false, boost3 = false;
+    PeakCoef p1, p2;
+    if (MASK & 1) {
+        s0_b0 = tp->eq[0].s[0].b0; s0_a1 = tp->eq[0].s[0].a1; s0_a2 = tp->eq[0].s[0].a2;
+        g0 = tp->eq[0].g; gm0 = tp->eq[0].gm1; boost0 = tp->eq[0].kind == AME_EQ_SHELF_BOOST;
+    }
+    if (MASK & 2) { load_peak(p1, tp->eq[1]); gm1 = tp->eq[1].gm1; }
+    if (MASK & 4) { load_peak(p2, tp->eq[2]); gm2 = tp->eq[2].gm1; }
+    if (MASK & 8) {
+        s3_b0 = tp->eq[3].s[0].b0; s3_a1 = tp->eq[3].s[0].a1; s3_a2 = tp->eq[3].s[0].a2;
+        g3 = tp->eq[3].g; gm3 = tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
+    }
     double zl[20], zr[20];
 #pragma unroll
     for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
 
+    const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
+    int64_t f_lo = job.tile_begin - warm;
+    if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
     const int64_t f_hi = job.tile_end;
-    int64_t f_lo, zero_before, next_reset = INT64_MAX;
-    const int64_t cf = tp->chunk_frames > 0 ? (int64_t)tp->chunk_frames : INT64_MAX / 4;
-    // K-weighting state (BS.1770 pre-filter: general biquad; RLB high-pass: numerator exactly 1 -2 1)
-    double kzl[4] = {0, 0, 0, 0}, kzr[4] = {0, 0, 0, 0}, accl = 0, accr = 0;
-    int pk = 0, sb = 0, n_sb = 0, s100 = 1, left = 1;
-    int64_t sb_off = 0;
-    if (KW) {
-        const int64_t track_begin = tp->offset_frames;     // no halo on tracks that take this path
-        const int64_t warm = ((MASK != 0) ? (int64_t)tp->warm_eq : 0) + (int64_t)tp->warm_kw;
-        f_lo = job.tile_begin - warm;
-        if (f_lo < track_begin) f_lo = track_begin;
-        zero_before = track_begin;
-        next_reset = track_begin + ((f_lo - track_begin) / cf + 1) * cf;     // first chunk start after f_lo
-        const TrackDev td = *tdp;
-        s100 = td.s100; n_sb = td.n_sb; sb_off = td.sb_offset;
-        sb = (int)((job.tile_begin - track_begin) / s100);  // tiles of this path start on the sub-block grid
-        left = s100;
-    } else {
-        const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
-        f_lo = job.tile_begin - warm;
-        if (f_lo < job.chunk_begin) f_lo = job.chunk_begin;
-        zero_before = job.chunk_begin;
-    }
     if (f_hi <= f_lo) return;
     const int64_t g0f = f_lo & ~(int64_t)3;               // first 4-aligned group
     const int n_it = (int)((f_hi - g0f + 3) >> 2);
 
     auto cascade = [&](double v, double *z) -> float {     // one channel through the 4 EQ stages
         if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
-            const double f = bw_step<1>(c.s0_b0, c.s0_a1, c.s0_a2, z[0], z[1], v);
-            v = boost0 ? v + (f - v) * c.gm0 : shelf_cut<true>(v, f, c.g0);
+            const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
+            v = boost0 ? v + (f - v) * gm0 : shelf_cut<true>(v, f, g0);
         }
-        if (MASK & 2) v = v + peak_step(c.p1_b0, c.p1_a1, c.p1_a2, z + 2, v) * c.gm1;    // apply_peak_filter 1 kHz (:290-298)
-        if (MASK & 4) v = v + peak_step(c.p2_b0, c.p2_a1, c.p2_a2, z + 10, v) * c.gm2;   // apply_peak_filter 4 kHz
+        if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
+        if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
         if (MASK & 8) {   // apply_shelf_filter 8 kHz high
-            const double f = bw_step<-1>(c.s3_b0, c.s3_a1, c.s3_a2, z[18], z[19], v);
-            v = boost3 ? v + (f - v) * c.gm3 : shelf_cut<(MASK & 7) == 0>(v, f, c.g3);
+            const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
+            v = boost3 ? v + (f - v) * gm3 : shelf_cut<(MASK & 7) == 0>(v, f, g3);
         }
         return __double2float_rn(v);                       // samples[:, i] = ... into the float32 array (:274)
     };
 
     // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
-    auto frame = [&](uint32_t w, double lutL, double lutR, int64_t f) -> uint32_t {
+    auto frame = [&](uint32_t w, double lutL, double lutR) -> uint32_t {
         int xl = (int)(int16_t)(w & 0xffffu), xr = (int)(int16_t)(w >> 16);
-        if (KW && f == next_reset) {                       // a chunk starts here: the reference restarts the EQ (:185-199)
-#pragma unroll
-            for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
-            next_reset += cf;
-        }
         if (WARM) {
             // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh, widened
             // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels:
             //   y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y - x)*(g - 1)       (no FMA contraction)
             double L = lutL, R = lutR;
-            double y0 = __dmul_rn(c.wl_b0, L);
-            double y1 = __dadd_rn(__dsub_rn(__dmul_rn(c.wl_b1, L), __dmul_rn(c.wl_a1, y0)), __dmul_rn(c.wl_b0, R));
-            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), c.wl_gm1));
-            const double R1 = __dadd_rn(R, __dmul_rn(__dsub_rn(y1, R), c.wl_gm1));
-            y0 = __dmul_rn(c.wh_b0, L1);
-            y1 = __dadd_rn(__dsub_rn(__dmul_rn(c.wh_b1, L1), __dmul_rn(c.wh_a1, y0)), __dmul_rn(c.wh_b0, R1));
-            L = __dadd_rn(L1, __dmul_rn(__dsub_rn(y0, L1), c.wh_gm1));
-            R = __dadd_rn(R1, __dmul_rn(__dsub_rn(y1, R1), c.wh_gm1));
+            double y0 = __dmul_rn(wl_b0, L);
+            double y1 = __dadd_rn(__dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0)), __dmul_rn(wl_b0, R));
+            const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), wl_gm1));
+            const double R1 = __dadd_rn(R, __dmul_rn(__dsub_rn(y1, R), wl_gm1));
+            y0 = __dmul_rn(wh_b0, L1);
+            y1 = __dadd_rn(__dsub_rn(__dmul_rn(wh_b1, L1), __dmul_rn(wh_a1, y0)), __dmul_rn(wh_b0, R1));
+            L = __dadd_rn(L1, __dmul_rn(__dsub_rn(y0, L1), wh_gm1));
+            R = __dadd_rn(R1, __dmul_rn(__dsub_rn(y1, R1), wh_gm1));
             xl = to_pcm_f64(L);                            // float_array_to_audio_segment (:254-257)
             xr = to_pcm_f64(R);
         }
@@ -260,33 +227,16 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const EqCfg &c, cons
             yl = __fadd_rn(mid, side);
             yr = __fsub_rn(mid, side);
         }
-        const int ol = to_pcm_f32(yl), orr = to_pcm_f32(yr);   // clip inside to_pcm == np.clip of (:270) then (:255)
-        if (KW) {
-            // ebur128 filter on x / 32768 (k_kweight_energy has the same arithmetic); energies only inside the tile
-            const double kl = bw_step1<-1>(c.k1a1, c.k1a2, kzl[2], kzl[3], kw_pre(c.k0b0, c.k0b1, c.k0b2, c.k0a1, c.k0a2, kzl[0], kzl[1], i16_to_unit(ol)));
-            const double kr = bw_step1<-1>(c.k1a1, c.k1a2, kzr[2], kzr[3], kw_pre(c.k0b0, c.k0b1, c.k0b2, c.k0a1, c.k0a2, kzr[0], kzr[1], i16_to_unit(orr)));
-            if (f >= job.tile_begin && f < f_hi) {
-                pk = max(pk, max(abs(ol), abs(orr)));
-                if (sb < n_sb) {
-                    accl = fma(kl, kl, accl);
-                    accr = fma(kr, kr, accr);
-                    if (--left == 0) {
-                        energy[sb_off + sb] = accl + accr;   // ebur128: per-channel sums, then added
-                        accl = 0; accr = 0; ++sb; left = s100;
-                    }
-                }
-            }
-        }
-        return pack16(ol, orr);
+        return pack16(to_pcm_f32(yl), to_pcm_f32(yr));     // clip inside to_pcm == np.clip of (:270) then (:255)
     };
 
     const uint4 *src = reinterpret_cast<const uint4 *>(in) + (g0f >> 2);
     uint4 *dst = reinterpret_cast<uint4 *>(pre) + (g0f >> 2);
     // software pipeline: input words two groups ahead, tanh-table values one group ahead
     uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
-    if (g0f + 0 < zero_before) cur.x = 0;                  // frames before the chunk (track) start keep the zero state
-    if (g0f + 1 < zero_before) cur.y = 0;
-    if (g0f + 2 < zero_before) cur.z = 0;
+    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // frames before the chunk start keep the zero state
+    if (g0f + 1 < job.chunk_begin) cur.y = 0;
+    if (g0f + 2 < job.chunk_begin) cur.z = 0;
     if (n_it > 1) nxt = ldg16(src + 1);
     double lutL[4] = {0, 0, 0, 0}, lutR[4] = {0, 0, 0, 0};
     auto fetch_lut = [&](const uint4 &q, double *l, double *r) {
@@ -307,7 +257,7 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const EqCfg &c, cons
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k], g + k);
+        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k]);
         if (g >= job.tile_begin && g + 4 <= f_hi) {
             dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
@@ -319,39 +269,25 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const EqCfg &c, cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutR[k] = nR[k]; }
     }
-    if (KW) atomicMax(peak + job.track, pk);
 }
 
-// Two entry points over the same job list: k_eq takes the tracks whose K-weighting is a separate pass (3 CTAs per SM:
-// with the coefficients in uniform registers the full cascade fits 168 vector registers), k_eq_kw the tracks that
-// measure in the epilogue (2 CTAs per SM).  A warp whose track belongs to the other kernel leaves at once.
-#define AME_EQ_KERNEL(NAME, KWF, MIN_CTAS)                                                                              \
-__global__ void __launch_bounds__(128, MIN_CTAS)                                                                        \
-NAME(const __grid_constant__ EqCfgTable tab, const TileJob *__restrict__ jobs, int n_jobs,                              \
-     const ame_track_params *__restrict__ tracks, const TrackDev *__restrict__ tdev, const double *__restrict__ luts,  \
-     const int16_t *__restrict__ in, int16_t *__restrict__ pre, double *__restrict__ energy, int *__restrict__ peak) { \
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;                                                                \
-    if (j >= n_jobs) return;              /* whole warps: every track's jobs are padded to a multiple of 32 */         \
-    const TileJob job = jobs[j];                                                                                        \
-    const TrackDev *td = tdev + job.track;                                                                              \
-    /* a warp's 32 jobs belong to ONE track: its configuration index is warp-uniform, provably so after the shuffle */ \
-    const int cfg = __shfl_sync(kFull, td->eq_cfg, 0);                                                                  \
-    if (job.tile_end <= job.tile_begin || ((job.variant & 32) != 0) != KWF) return;   /* padding / the other kernel's */ \
-    const ame_track_params *tp = tracks + job.track;                                                                    \
-    const EqCfg &c = tab.c[cfg];                                                                                        \
-    switch (job.variant & 31) {           /* bits 0-3: EQ stages, bit 4: warmth */                                      \
-        AME_EQ_CASE(0, KWF) AME_EQ_CASE(1, KWF) AME_EQ_CASE(2, KWF) AME_EQ_CASE(3, KWF) AME_EQ_CASE(4, KWF)             \
-        AME_EQ_CASE(5, KWF) AME_EQ_CASE(6, KWF) AME_EQ_CASE(7, KWF) AME_EQ_CASE(8, KWF) AME_EQ_CASE(9, KWF)             \
-        AME_EQ_CASE(10, KWF) AME_EQ_CASE(11, KWF) AME_EQ_CASE(12, KWF) AME_EQ_CASE(13, KWF) AME_EQ_CASE(14, KWF)        \
-        AME_EQ_CASE(15, KWF)                                                                                            \
-    }                                                                                                                   \
-}
-#define AME_EQ_CASE(M, KWF) case M: eq_tile<M, false, KWF>(job, c, tp, td, luts, in, pre, energy, peak); break;       \
-                            case M + 16: eq_tile<M, true, KWF>(job, c, tp, td, luts, in, pre, energy, peak); break;
-AME_EQ_KERNEL(k_eq, false, 3)
-AME_EQ_KERNEL(k_eq_kw, true, 2)
+__global__ void __launch_bounds__(128, 2)
+k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const TileJob job = jobs[j];
+    if (job.tile_end <= job.tile_begin) return;           // padding job (tracks get whole warps)
+    const ame_track_params *tp = tracks + job.track;
+    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth
+#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre); break; \
+                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre); break;
+        AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
+        AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
+        AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
 #undef AME_EQ_CASE
-#undef AME_EQ_KERNEL
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_band_split: int16 pre -> Butterworth-4 LP 250 / HP 4k in FP64, mid = x - low - high, each band
@@ -363,7 +299,7 @@ struct XoverCfg { double lb0, la10, la20, la11, la21, hb0, ha10, ha20, ha11, ha2
 // UNI: every multiband track of the launch has the same crossover (same sample rate) - the usual case; the
 // coefficients then come from the kernel parameter and live in uniform registers.
 template <bool UNI>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 k_band_split(const __grid_constant__ XoverCfg xc, const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
              const int64_t *__restrict__ mb_delta,   // per track: mb_offset - offset_frames
              const int16_t *__restrict__ pre, int16_t *__restrict__ bands, int64_t mb_frames) {
@@ -913,7 +849,7 @@ __device__ __noinline__ double gain_of_att(double att) { return exp10(-att / 20.
 // list value of the last flagged frame at or before it: rank = group base + popc(mask up to the lane); 0 before the
 // first flagged frame of the chunk.  gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)),
 // skipped when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
                  const int16_t *__restrict__ bands, const GrpRec *__restrict__ grp, const double *__restrict__ att,
                  int16_t *__restrict__ pre, int64_t mb_frames) {

@@ -40,7 +40,7 @@ class MasterPlan:
 
     def __init__(self, lengths, sample_rates, settings_list, device=0, chunk_seconds=30, host_io=False,
                  eq_tile_frames=0, xover_tile_frames=0, kw_tile_subblocks=0, halos=None, n_waves=1, chain_warps=0,
-                 n_slots=0, fuse_kw=False, precision="exact"):
+                 n_slots=0, precision="exact"):
         self.lib = L.load()
         n = len(lengths)
         if n == 0:
@@ -65,7 +65,7 @@ class MasterPlan:
                                          chunk_seconds, lut_index, self.halos[i])
         self.params = arr
         opt = L.PlanOptions(int(eq_tile_frames), int(xover_tile_frames), int(kw_tile_subblocks), 1 if host_io else 0,
-                            int(n_waves), int(chain_warps), int(n_slots), 1 if fuse_kw else 0,
+                            int(n_waves), int(chain_warps), int(n_slots),
                             {"exact": 0, "fp32": 1}[precision])
         h = C.c_void_p()
         L.check(self.lib.ame_plan_create(int(device), arr, n, C.byref(opt), C.byref(h)))

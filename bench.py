@@ -52,7 +52,6 @@ def parse():
     ap.add_argument("--chain-warps", type=int, default=0, help="ame_plan_options.chain_warps (0 = auto, -1 = queue kernel)")
     ap.add_argument("--waves", type=int, default=6, help="plan waves of the device-resident path")
     ap.add_argument("--slots", type=int, default=0, help="workspace slots (0 = min(waves, 4))")
-    ap.add_argument("--fuse-kw", action="store_true", help="K-weighting in the k_eq epilogue for tracks without multiband (A/B)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -200,7 +199,7 @@ def run_b200(args, rank, world, local_rank):
     settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
     plan = MasterPlan([n] * n_tr, fs, settings, device=local_rank, n_waves=args.waves, chain_warps=args.chain_warps,
                       kw_tile_subblocks=args.kw_tile, eq_tile_frames=args.eq_tile, xover_tile_frames=args.xover_tile,
-                      n_slots=args.slots, fuse_kw=args.fuse_kw)
+                      n_slots=args.slots)
     assert plan.total_frames == n_tr * ((n + 7) // 8 * 8)
     tracks = synth.torch_track_batch(n_tr, secs, fs, dev, first_track_id=first)        # [n_tr, n, 2] int16
     d_in = torch.zeros((plan.total_frames, 2), dtype=torch.int16, device=dev)

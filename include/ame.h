@@ -134,9 +134,6 @@ typedef struct {
     int32_t n_slots;             /* workspace slots: wave w runs in slot w % n_slots on that slot's stream, so only
                                     n_slots waves are in flight and the plan's workspace is that of n_slots waves, not
                                     of the batch (1024 tracks fit one GPU).  <= 0: min(n_waves, 4) */
-    int32_t fuse_kw;             /* 1 = tracks without a multiband stage get their K-weighting / 100 ms energies in
-                                    the k_eq epilogue (the pre-normalisation signal is not read again; pays when tiles
-                                    are much longer than the K filter's warm-up); 0 = the separate k_kweight_energy pass */
     int32_t precision;           /* 0 = FP64 filters (results equal to the reference's float64 scipy path);
                                     1 = EQ cascade in FP32 (A/B measurement only: +-1 LSB truncation flips, which the
                                     make-up gain of the loudness stage multiplies - DESIGN.md) */
