@@ -7,8 +7,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libame.so")
 
-AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE = 1, 2, 4, 8
-AME_N_KERNELS = 10
+AME_F_WARMTH, AME_F_WIDTH, AME_F_MULTIBAND, AME_F_NORMALIZE, AME_F_LIMITER, AME_F_TRUE_PEAK = 1, 2, 4, 8, 16, 32
+AME_N_KERNELS = 12
 AME_EQ_BYPASS, AME_EQ_SHELF_BOOST, AME_EQ_SHELF_CUT, AME_EQ_PEAK = 0, 1, 2, 3
 AME_ABI_VERSION = 5
 
@@ -35,13 +35,15 @@ class TrackParams(C.Structure):
                 ("eq", EqStage * 4), ("width", C.c_float), ("pad0_", C.c_float),
                 ("xlp", Biquad * 2), ("xhp", Biquad * 2), ("comp", CompBand * 3), ("kw", Biquad * 2),
                 ("target_lufs", C.c_double), ("warm_eq", C.c_int32), ("warm_xover", C.c_int32),
-                ("warm_kw", C.c_int32), ("pad1_", C.c_int32)]
+                ("warm_kw", C.c_int32), ("lim_frames", C.c_int32), ("lim_limit", C.c_double), ("lim_level", C.c_double),
+                ("lim_fs_release", C.c_double), ("lim_release_frames", C.c_int32), ("lim_thr_i", C.c_int32)]
 
 
 class TrackResult(C.Structure):
     _fields_ = [("input_i", C.c_double), ("measured_i_2dp", C.c_double), ("gain", C.c_double),
                 ("rel_threshold", C.c_double), ("n_blocks", C.c_int64), ("normalized", C.c_int32),
-                ("sample_peak", C.c_int32), ("input_lra", C.c_double), ("input_thresh", C.c_double)]
+                ("sample_peak", C.c_int32), ("input_lra", C.c_double), ("input_thresh", C.c_double),
+                ("true_peak", C.c_double)]
 
 
 class PlanOptions(C.Structure):

@@ -112,12 +112,12 @@ int upload(T **dptr, const std::vector<T> &v) {
     return AME_OK;
 }
 
-constexpr int kMaxTimedSteps = 64;
-constexpr int kMaxTimedWaves = 16;
+constexpr int kMaxTimedSteps = 8;
+constexpr int kMaxTimedWaves = 128;
 constexpr int kTimedSlots = kMaxTimedWaves * AME_N_KERNELS;   // per step
 const char *const kKernelNames[AME_N_KERNELS] = {"k_eq", "k_band_split", "k_window_flag", "k_att_chain",
-    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain"};
-enum { S_EQ = 0, S_SPLIT, S_FLAG, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN };
+    "k_compress_apply", "k_kweight_energy", "k_tail_peak", "k_block_hist", "k_finalize", "k_apply_gain", "k_limiter", "k_true_peak"};
+enum { S_EQ = 0, S_SPLIT, S_FLAG, S_CHAIN, S_APPLY, S_KW, S_TAIL, S_HIST, S_FIN, S_GAIN, S_LIM, S_TP };
 
 // A wave = a contiguous range of tracks whose jobs are contiguous in every job table.  The device path
 // launches each kernel ONCE over all waves; the host path (ame_master_host) launches wave by wave so the
@@ -129,6 +129,7 @@ struct Wave {
     int chunk_lo = 0, chunk_n = 0, kw_lo = 0, kw_n = 0, gain_lo = 0, gain_n = 0;
     int64_t seg_lo = 0, seg_hi = 0;
     int slot = 0;                                  // workspace slot (and stream) this wave runs in
+    bool limiter = false;                          // a track of the wave has the limiter stage
     int64_t mb_frames = 0, n_groups = 0;           // of the wave's own multiband packing
     bool xover_uni = false, kw_uni = false;        // all multiband tracks share the crossover / all k_kweight_energy tracks the K filter
     XoverCfg xover{};
@@ -146,6 +147,8 @@ struct Slot {
     int *n_flagged = nullptr;    // flagged frames per chain
     GrpRec *grp = nullptr;       // per 32-frame group of every chain
     double *att = nullptr;       // 3 planes: attenuation after every flagged frame, dense per chain
+    int16_t *norm = nullptr;     // the normalised signal of tracks with the limiter stage (k_apply_gain -> k_limiter)
+    long long *lim_last = nullptr;   // per k_apply_gain tile: last frame over the limiter's limit, or -1
     cudaStream_t stream = nullptr;
 };
 
@@ -188,6 +191,9 @@ struct ame_plan {
     long long *d_hist = nullptr;
     int *d_hist_st = nullptr;               // short-term (3 s) histogram per track, for loudness range
     int *d_peak = nullptr;
+    unsigned *d_tp = nullptr;               // per track: float bits of the oversampled peak (k_true_peak)
+    bool any_limiter = false, any_tp = false;
+    int slot_gain_jobs = 0;
     ame_track_result *d_results = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
     std::vector<cudaEvent_t> ev_in, ev_run;                             // per wave
@@ -316,6 +322,15 @@ int validate(const ame_track_params &t, int idx) {
         return fail(AME_E_INVALID, "track %d: halo_frames must be a multiple of 8 and of the 100 ms sub-block", idx);
     if (t.warm_eq < 0 || t.warm_xover < 0 || t.warm_kw < 0)
         return fail(AME_E_INVALID, "track %d: negative warm-up", idx);
+    if (t.flags & AME_F_LIMITER) {
+        if (t.halo_frames)
+            return fail(AME_E_UNSUPPORTED, "track %d: the limiter is one sequential state machine over the whole track and cannot "
+                                           "run on a time shard; limit the gathered output instead", idx);
+        if (t.lim_frames < 1 || t.lim_frames > kLimQueue - 24 || !(t.lim_limit > 0.0 && t.lim_limit <= 1.0) || !(t.lim_fs_release > 0.0) ||
+            t.lim_release_frames < 1 || t.lim_frames + t.lim_release_frames + 8 > kGainTile || t.lim_thr_i < 1)
+            return fail(AME_E_INVALID, "track %d: bad limiter parameters (look-ahead %d frames, release %d frames)", idx, t.lim_frames,
+                        t.lim_release_frames);
+    }
     for (int s = 0; s < 4; ++s) {
         const int k = t.eq[s].kind;
         const bool shelf = (s == 0 || s == 3);
@@ -398,6 +413,8 @@ struct Bufs {
     GrpRec *grp = nullptr;
     double *att = nullptr;
     int64_t *hist = nullptr;
+    int16_t *norm = nullptr;
+    long long *lim_last = nullptr;
 };
 
 Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) {
@@ -407,6 +424,8 @@ Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) 
     b.pre = sl.pre - 2 * w.frame_lo;
     b.bands = sl.bands; b.rms = sl.rms; b.list = sl.list; b.tile_cnt = sl.tile_cnt; b.n_flagged = sl.n_flagged;
     b.grp = sl.grp; b.att = sl.att;
+    b.norm = sl.norm ? sl.norm - 2 * w.frame_lo : nullptr;
+    b.lim_last = sl.lim_last;
     b.hist = (int64_t *)p->d_hist;
     return b;
 }
@@ -485,6 +504,13 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     k_tail_peak<<<nt, 128, 0, s>>>(p->d_tracks, p->d_tdev, w.track_lo, w.track_hi, d_pre, p->d_peak);
     LAUNCH_CHECK(p);
     t_end(p, S_TAIL, s);
+    CU(cudaMemsetAsync(p->d_tp + w.track_lo, 0, (size_t)nt * 4, s));
+    if (p->any_tp && w.gain_n) {
+        t_begin(p, S_TP, s);
+        k_true_peak<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_tracks, d_pre, p->d_tp);
+        LAUNCH_CHECK(p);
+        t_end(p, S_TP, s);
+    }
     t_begin(p, S_HIST, s);
     k_block_hist<<<nt, 256, 0, s>>>(p->d_tdev, w.track_lo, p->d_energy, (long long *)d_hist, p->d_hist_st);
     LAUNCH_CHECK(p);
@@ -492,18 +518,26 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     return AME_OK;
 }
 
-int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, cudaStream_t s) {
+int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, int16_t *d_norm,
+             long long *lim_last, cudaStream_t s) {
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
     t_begin(p, S_FIN, s);
-    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_hist_st, p->d_peak, p->d_results);
+    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_hist_st, p->d_peak,
+                                             p->d_tp, p->d_results);
     LAUNCH_CHECK(p);
     t_end(p, S_FIN, s);
     if (w.gain_n) {
         t_begin(p, S_GAIN, s);
-        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, d_pre, d_out);
+        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, p->d_tracks, d_pre, d_out, d_norm, lim_last);
         LAUNCH_CHECK(p);
         t_end(p, S_GAIN, s);
+        if (w.limiter) {
+            t_begin(p, S_LIM, s);
+            k_limiter<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, w.gain_n, lim_last, p->d_tracks, d_norm, d_out);
+            LAUNCH_CHECK(p);
+            t_end(p, S_LIM, s);
+        }
     }
     return AME_OK;
 }
@@ -519,7 +553,7 @@ int run_measure(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
 int run_chain_of_stages(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     int rc = run_measure(p, w, b, s);
     if (rc) return rc;
-    return run_gain(p, w, b.pre, b.hist, b.out, s);
+    return run_gain(p, w, b.pre, b.hist, b.out, b.norm, b.lim_last, s);
 }
 
 // after a failure in the middle of a pipelined call nothing may still be reading the caller's buffers when we return
@@ -552,13 +586,13 @@ void ame_plan_destroy(ame_plan *p) {
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts,
-                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_results,
+                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_tp, p->d_results,
                     p->d_chain_stats};
     cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
     for (void *q : ptrs) dev_free(q);
     for (Slot &sl : p->slots) {
         for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.list, (void *)sl.tile_cnt, (void *)sl.n_flagged,
-                        (void *)sl.grp, (void *)sl.att})
+                        (void *)sl.grp, (void *)sl.att, (void *)sl.norm, (void *)sl.lim_last})
             dev_free(q);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -613,6 +647,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
         p->tdev[t].pad = 0;
+        p->any_limiter = p->any_limiter || (tp.flags & AME_F_LIMITER);
+        p->any_tp = p->any_tp || (tp.flags & AME_F_TRUE_PEAK);
     }
     for (size_t i = 1; i < spans.size(); ++i)
         if (spans[i].first < align_up(spans[i - 1].second, 8)) return bail(fail(AME_E_INVALID, "tracks overlap in the packed buffer"));
@@ -840,6 +876,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
         wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
         wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) wv.limiter = wv.limiter || (p->tracks[t].flags & AME_F_LIMITER);
+        p->slot_gain_jobs = std::max(p->slot_gain_jobs, wv.gain_n);
         p->slot_tiles = std::max(p->slot_tiles, wv.wf_n);
         p->slot_chains = std::max(p->slot_chains, wv.chain_n);
     }
@@ -862,6 +900,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             (rc = dmalloc(p, (void **)&sl.grp, (size_t)p->slot_groups * sizeof(GrpRec))) ||
             (rc = dmalloc(p, (void **)&sl.att, (size_t)p->mb_frames * 8 * 3)))
             return bail(rc);
+        if (p->any_limiter &&
+            ((rc = dmalloc(p, (void **)&sl.norm, (size_t)p->slot_frames * 4)) ||
+             (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(long long)))))
+            return bail(rc);
         // the filters read a few frames past a track's end (whole 16 / 32-byte groups, never stored): keep them defined
         if (cudaMemsetAsync(sl.pre, 0, (size_t)p->slot_frames * 4, 0) != cudaSuccess ||
             (p->mb_frames && cudaMemsetAsync(sl.bands, 0, (size_t)p->mb_frames * 12, 0) != cudaSuccess))
@@ -872,6 +914,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         (rc = dmalloc(p, (void **)&p->d_hist, (size_t)n_tracks * 1000 * 8)) ||
         (rc = dmalloc(p, (void **)&p->d_hist_st, (size_t)n_tracks * 1000 * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
+        (rc = dmalloc(p, (void **)&p->d_tp, (size_t)n_tracks * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_results, (size_t)n_tracks * sizeof(ame_track_result))))
         return bail(rc);
     if (cudaMemsetAsync(p->d_chain_stats, 0, std::max<size_t>(chain_jobs.size(), 1) * 2 * sizeof(int), 0) != cudaSuccess)
@@ -1070,7 +1113,8 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
     SINGLE_WAVE(p);
     GUARD(p->device);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = run_gain(p, p->waves[0], d_pre, d_hist, d_out, s);
+    const Bufs sb = slot_bufs(p, p->waves[0], nullptr, d_out);
+    int rc = run_gain(p, p->waves[0], d_pre, d_hist, d_out, sb.norm, sb.lim_last, s);
     if (rc) return rc;
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
@@ -1106,7 +1150,7 @@ int ame_normalize_device(ame_plan *p, const int64_t *d_hist, int16_t *d_out, ame
     for (size_t w = 0; w < p->waves.size(); ++w) {
         p->t_wave = (int)std::min<size_t>(w, kMaxTimedWaves - 1);
         const Bufs b = slot_bufs(p, p->waves[w], nullptr, d_out);
-        if ((rc = run_gain(p, p->waves[w], b.pre, d_hist, d_out, s))) return rc;
+        if ((rc = run_gain(p, p->waves[w], b.pre, d_hist, d_out, b.norm, b.lim_last, s))) return rc;
     }
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));

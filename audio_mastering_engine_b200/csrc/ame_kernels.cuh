@@ -849,7 +849,7 @@ __device__ __noinline__ double gain_of_att(double att) { return exp10(-att / 20.
 // list value of the last flagged frame at or before it: rank = group base + popc(mask up to the lane); 0 before the
 // first flagged frame of the chunk.  gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)),
 // skipped when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128)
 k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
                  const int16_t *__restrict__ bands, const GrpRec *__restrict__ grp, const double *__restrict__ att,
                  int16_t *__restrict__ pre, int64_t mb_frames) {
@@ -1031,7 +1031,7 @@ k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__re
 // k_finalize: ebur128_gated_loudness + loudness range + the linear-mode gain of af_loudnorm, one thread per track
 __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_hi,
                            const long long *__restrict__ hist, const int *__restrict__ hist_st, const int *__restrict__ peak,
-                           ame_track_result *__restrict__ res) {
+                           const unsigned *__restrict__ tp_bits, ame_track_result *__restrict__ res) {
     const int t = track_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= track_hi) return;
     const long long *h = hist + (int64_t)t * 1000;
@@ -1039,6 +1039,8 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
     r.input_i = -INFINITY; r.measured_i_2dp = -INFINITY; r.gain = 1.0; r.rel_threshold = 0.0;
     r.n_blocks = 0; r.normalized = 0; r.sample_peak = peak[t];
     r.input_lra = 0.0; r.input_thresh = -70.0;
+    r.true_peak = ((tracks[t].flags & AME_F_TRUE_PEAK) && tracks[t].sample_rate < 192000) ? (double)__uint_as_float(tp_bits[t])
+                                                                                           : (double)peak[t] * (1.0 / 32768.0);
     double rel = 0.0; long long count = 0;
     for (int j = 0; j < 1000; ++j) { rel += (double)h[j] * c_hist_energy[j]; count += h[j]; }
     r.n_blocks = count;
@@ -1089,32 +1091,248 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
     res[t] = r;
 }
 
-// k_apply_gain: loudnorm linear mode: s16 -> x/32768 -> * gain -> lrint(x * 32768) clipped to s16
+// k_apply_gain: loudnorm linear mode: s16 -> x/32768 -> * gain -> lrint(x * 32768) clipped to s16.
+// Tracks with the limiter stage write the normalised signal to the slot's `norm` buffer instead of `out` (k_limiter
+// reads it) and record per tile the last frame whose peak exceeds the limiter's limit.
 __global__ void __launch_bounds__(256)
-k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restrict__ res,
-             const int16_t *__restrict__ pre, int16_t *__restrict__ out) {
+k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restrict__ res, const ame_track_params *__restrict__ tracks,
+             const int16_t *__restrict__ pre, int16_t *__restrict__ out, int16_t *__restrict__ norm, long long *__restrict__ lim_last) {
+    __shared__ long long s_last;
     const GainJob job = jobs[blockIdx.x];
     const ame_track_result r = res[job.track];
+    const bool lim = (tracks[job.track].flags & AME_F_LIMITER) != 0;
+    const int thr_i = tracks[job.track].lim_thr_i;
     const uint4 *src = reinterpret_cast<const uint4 *>(pre);
-    uint4 *dst = reinterpret_cast<uint4 *>(out);
+    uint4 *dst = reinterpret_cast<uint4 *>(lim ? norm : out);
     const int64_t v0 = job.begin >> 2, v1 = (job.end + 3) >> 2;   // 4 frames per uint4; tiles are 4-aligned
-    if (!r.normalized) {
-        for (int64_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) dst[v] = __ldg(src + v);
-        return;
-    }
+    if (lim && threadIdx.x == 0) s_last = -1;
+    if (lim) __syncthreads();
+    long long last = -1;
     const double g = r.gain;
     for (int64_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
         const uint4 q = __ldg(src + v);
         uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        if (r.normalized) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int l = (int16_t)(w[k] & 0xffffu), rr = (int16_t)(w[k] >> 16);
-            int ol = __double2int_rn(__dmul_rn(__dmul_rn((double)l * (1.0 / 32768.0), g), 32768.0));
-            int orr = __double2int_rn(__dmul_rn(__dmul_rn((double)rr * (1.0 / 32768.0), g), 32768.0));
-            w[k] = (uint32_t)(uint16_t)sat16(ol) | ((uint32_t)(uint16_t)sat16(orr) << 16);
+            for (int k = 0; k < 4; ++k) {
+                const int l = (int16_t)(w[k] & 0xffffu), rr = (int16_t)(w[k] >> 16);
+                int ol = __double2int_rn(__dmul_rn(__dmul_rn((double)l * (1.0 / 32768.0), g), 32768.0));
+                int orr = __double2int_rn(__dmul_rn(__dmul_rn((double)rr * (1.0 / 32768.0), g), 32768.0));
+                w[k] = (uint32_t)(uint16_t)sat16(ol) | ((uint32_t)(uint16_t)sat16(orr) << 16);
+            }
+        }
+        if (lim) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int l = (int16_t)(w[k] & 0xffffu), rr = (int16_t)(w[k] >> 16);
+                const int64_t f = 4 * v + k;
+                if (max(abs(l), abs(rr)) >= thr_i && f >= job.begin && f < job.end) last = f;
+            }
         }
         dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (lim) {
+        if (last >= 0) atomicMax(&s_last, last);
+        __syncthreads();
+        if (threadIdx.x == 0) lim_last[blockIdx.x] = s_last;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_limiter: ffmpeg alimiter (audio_mastering_engine.py:223; af_alimiter.c with level_in = level_out = 1, auto level
+// on, asc off, latency off) on the normalised signal.  The filter is one sequential state machine per track:
+// a look-ahead ring of B frames (output = input delayed by B - 1 frames), an attenuation `att` that moves by `delta`
+// per frame, and a queue of the over-limit peaks inside the ring with the slope each will hand over when it leaves.
+// What makes it parallel in time: after G = B + release_frames + 8 frames without an over-limit frame the state is
+// the initial one again (att 1, delta 0, empty queue - the last queued peak has left the ring and its linear release
+// has reached 1), and in that state the filter is elementwise: out[n] = clip(x[n - B + 1]) / limit.
+// One CTA per k_apply_gain tile (32768 frames >= G):
+//   * a tile that starts in the initial state (no over-limit frame in the G frames before it: k_apply_gain left
+//     the previous tile's last over-limit frame) and has no over-limit frame of its own is done elementwise by all
+//     256 threads;
+//   * a tile that starts in the initial state and has over-limit frames makes warp 0 the sequential machine from its
+//     first frame up to the next tile that starts in the initial state (lane 0 walks the attenuation 32 frames at a
+//     time, all lanes load the frames before and scale / round / store them after);
+//   * every other tile is covered by such a run and its CTA leaves at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLimQueue = 1024;     // queue capacity >= B + 2 (B <= 1000 frames is validated by the host)
+
+__device__ __forceinline__ int lim_out_sample(int x, double att, double limit, double level) {
+    double v = __dmul_rn((double)x * (1.0 / 32768.0), att);          // buf[c] * att
+    v = fmin(fmax(v, -limit), limit);                                 // av_clipd(dst, -limit, limit)
+    v = __dmul_rn(v, level);                                          // * level (* level_out = 1)
+    return sat16(__double2int_rn(__dmul_rn(v, 32768.0)));             // swresample dbl -> s16
+}
+
+__global__ void __launch_bounds__(256)
+k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restrict__ lim_last,
+          const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ norm, int16_t *__restrict__ out) {
+    __shared__ int s_qframe[kLimQueue];           // frame (relative to the track start) of every queued peak, -1 = none
+    __shared__ double s_qdelta[kLimQueue];
+    __shared__ double s_att[32];
+    __shared__ int s_pin[32], s_pout[32];         // peak (max |s16|) of the frame entering / leaving the ring at each step
+    const GainJob job = jobs[blockIdx.x];
+    const ame_track_params *tp = tracks + job.track;
+    if (!(tp->flags & AME_F_LIMITER)) return;
+    const int B = tp->lim_frames;
+    const double limit = tp->lim_limit, level = tp->lim_level, fsrel = tp->lim_fs_release;
+    const int64_t G = (int64_t)B + tp->lim_release_frames + 8;
+    const int64_t t_begin = tp->offset_frames + tp->halo_frames, t_end = t_begin + tp->n_frames;
+    const bool first = blockIdx.x == 0 || jobs[blockIdx.x - 1].track != job.track;
+    const long long prev_last = first ? -1 : lim_last[blockIdx.x - 1];
+    const bool quiet_start = first || prev_last < 0 || (job.begin - 1 - prev_last >= G);
+    if (!quiet_start) return;                                         // inside some earlier tile's sequential run
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(norm);
+    uint32_t *y = reinterpret_cast<uint32_t *>(out);
+    auto emit = [&](int64_t n, double att) {                          // output frame n = input frame n - (B - 1)
+        const int64_t m = n - (B - 1);
+        const uint32_t w = m >= t_begin ? __ldg(x + m) : 0u;
+        y[n] = pack16(lim_out_sample((int16_t)(w & 0xffffu), att, limit, level), lim_out_sample((int16_t)(w >> 16), att, limit, level));
+    };
+    if (lim_last[blockIdx.x] < 0) {                                   // initial state throughout: elementwise
+        for (int64_t n = job.begin + threadIdx.x; n < job.end; n += blockDim.x) emit(n, 1.0);
+        return;
+    }
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int thr_i = tp->lim_thr_i;
+    for (int i = lane; i < kLimQueue; i += 32) { s_qframe[i] = -1; s_qdelta[i] = 0.0; }
+    __syncwarp();
+    // lane 0's state (af_alimiter.c: att, delta, nextiter, nextlen; nextpos / nextdelta are s_qframe / s_qdelta)
+    double att = 1.0, delta = 0.0;
+    int qiter = 0, qlen = 0;
+    int64_t last_over = -1;
+    const int bufsize = 2 * B;
+    auto peak_of = [&](int64_t rel) -> double {                       // |sample| peak of a frame of the track, as the ring holds it
+        const uint32_t w = __ldg(x + t_begin + rel);
+        const int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
+        return (double)max(abs(l), abs(r)) * (1.0 / 32768.0);
+    };
+    bool done = false;
+    for (int64_t n0 = job.begin; n0 < t_end && !done; n0 += 32) {
+        const int64_t n = n0 + lane, m = n - (B - 1);
+        const uint32_t win = n < t_end ? __ldg(x + n) : 0u;
+        const uint32_t wout = (n < t_end && m >= t_begin) ? __ldg(x + m) : 0u;
+        s_pin[lane] = max(abs((int)(int16_t)(win & 0xffffu)), abs((int)(int16_t)(win >> 16)));
+        s_pout[lane] = max(abs((int)(int16_t)(wout & 0xffffu)), abs((int)(int16_t)(wout >> 16)));
+        const unsigned over = __ballot_sync(kFull, n < t_end && s_pin[lane] >= thr_i);
+        __syncwarp();
+        int n_valid = (int)min((int64_t)32, t_end - n0);
+        if (lane == 0) {
+            for (int k = 0; k < n_valid; ++k) {
+                const int64_t nn = n0 + k;
+                const int rel = (int)(nn - t_begin);
+                if (over & (1u << k)) {                               // the entering frame is over the limit
+                    last_over = nn;
+                    const double peak = (double)s_pin[k] * (1.0 / 32768.0);
+                    const double patt = fmin(limit / peak, 1.0);
+                    const double rdelta = (1.0 - patt) / fsrel;
+                    const double d = (limit / peak - att) / bufsize * 2;
+                    if (d < delta) {
+                        delta = d;
+                        s_qframe[0] = rel; s_qframe[1] = -1; s_qdelta[0] = rdelta;
+                        qlen = 1; qiter = 0;
+                    } else {
+                        bool found = false;
+                        int i = qiter;
+                        for (; i < qiter + qlen; ++i) {
+                            const int j = i % kLimQueue;
+                            const double ppeak = peak_of(s_qframe[j]);
+                            const double pdelta = (limit / peak - limit / ppeak) / (double)(rel - s_qframe[j]);
+                            if (pdelta < s_qdelta[j]) { s_qdelta[j] = pdelta; found = true; break; }
+                        }
+                        if (found) {
+                            qlen = i - qiter + 1;
+                            s_qframe[(qiter + qlen) % kLimQueue] = rel;
+                            s_qdelta[(qiter + qlen) % kLimQueue] = rdelta;
+                            s_qframe[(qiter + qlen + 1) % kLimQueue] = -1;
+                            ++qlen;
+                        }
+                    }
+                }
+                att += delta;
+                s_att[k] = att;                                       // the leaving frame is scaled by this
+                if (rel >= B - 1 && rel - (B - 1) == s_qframe[qiter]) {   // a queued peak leaves the ring
+                    delta = s_qdelta[qiter];
+                    att = limit / ((double)s_pout[k] * (1.0 / 32768.0));
+                    --qlen;
+                    s_qframe[qiter] = -1;
+                    qiter = (qiter + 1) % kLimQueue;
+                }
+                if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; s_qframe[0] = -1; }
+                if (att <= 0.0) { att = 0.0000000000001; delta = (1.0 - att) / fsrel; }
+                if (att != 1.0 && (1.0 - att) < 0.0000000000001) att = 1.0;
+                if (delta != 0.0 && fabs(delta) < 0.00000000000001) delta = 0.0;
+                // end of a tile: does the next one start in the initial state?  (the same test its own CTA makes)
+                if ((nn + 1 - t_begin) % kGainTile == 0 && nn + 1 < t_end) {
+                    const int64_t tile_lo = nn + 1 - kGainTile;
+                    if (last_over < tile_lo || nn - last_over >= G) { n_valid = k + 1; done = true; break; }
+                }
+            }
+        }
+        n_valid = __shfl_sync(kFull, n_valid, 0);
+        done = __shfl_sync(kFull, (int)done, 0) != 0;
+        __syncwarp();
+        if (lane < n_valid) emit(n, s_att[lane]);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_true_peak: ITU-R BS.1770-4 Annex 2 true-peak estimate of the pre-normalisation signal (what loudnorm's
+// measured_TP / the linear-mode test TP=-1.5 at :229,240 stand on): the signal oversampled 4x (fs < 96 kHz), 2x
+// (fs < 192 kHz) or taken as is, by the 4-phase x 12-tap interpolator of the recommendation, maximum |y| over both
+// channels.  One CTA per k_apply_gain tile; float32 arithmetic (a level meter, not on the audio path).
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_tp_fir[4][12] = {
+    {0.0017089843750f, 0.0109863281250f, -0.0196533203125f, 0.0332031250000f, -0.0594482421875f, 0.1373291015625f,
+     0.9721679687500f, -0.1022949218750f, 0.0476074218750f, -0.0266113281250f, 0.0148925781250f, -0.0083007812500f},
+    {-0.0291748046875f, 0.0292968750000f, -0.0517578125000f, 0.0891113281250f, -0.1665039062500f, 0.4650878906250f,
+     0.7797851562500f, -0.2003173828125f, 0.1015625000000f, -0.0582275390625f, 0.0330810546875f, -0.0189208984375f},
+    {-0.0189208984375f, 0.0330810546875f, -0.0582275390625f, 0.1015625000000f, -0.2003173828125f, 0.7797851562500f,
+     0.4650878906250f, -0.1665039062500f, 0.0891113281250f, -0.0517578125000f, 0.0292968750000f, -0.0291748046875f},
+    {-0.0083007812500f, 0.0148925781250f, -0.0266113281250f, 0.0476074218750f, -0.1022949218750f, 0.9721679687500f,
+     0.1373291015625f, -0.0594482421875f, 0.0332031250000f, -0.0196533203125f, 0.0109863281250f, 0.0017089843750f}};
+
+__global__ void __launch_bounds__(256)
+k_true_peak(const GainJob *__restrict__ jobs, const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ pre,
+            unsigned *__restrict__ tp_bits) {
+    const GainJob job = jobs[blockIdx.x];
+    const ame_track_params *tp = tracks + job.track;
+    if (!(tp->flags & AME_F_TRUE_PEAK)) return;
+    const int fs = tp->sample_rate;
+    if (fs >= 192000) return;                                          // no oversampling: k_finalize reports the sample peak
+    const int step = fs < 96000 ? 1 : 2;                               // phases 0,1,2,3 (4x) or 0,2 (2x)
+    const int64_t t_begin = tp->offset_frames + tp->halo_frames;
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(pre);
+    float best = 0.0f;
+    // 8 frames per thread and iteration, 11 frames of history in front
+    for (int64_t n0 = job.begin + (int64_t)threadIdx.x * 8; n0 < job.end; n0 += (int64_t)blockDim.x * 8) {
+        float l[19], r[19];
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const int64_t m = n0 - 11 + k;
+            const uint32_t w = (m >= t_begin && m < job.end) ? __ldg(x + m) : 0u;
+            l[k] = (float)(int16_t)(w & 0xffffu) * (1.0f / 32768.0f);
+            r[k] = (float)(int16_t)(w >> 16) * (1.0f / 32768.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (n0 + i >= job.end) break;
+            for (int p = 0; p < 4; p += step) {
+                float yl = 0.0f, yr = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {                        // y[4n + p] = sum_k h_p[k] x[n - k]
+                    yl = fmaf(c_tp_fir[p][k], l[11 + i - k], yl);
+                    yr = fmaf(c_tp_fir[p][k], r[11 + i - k], yr);
+                }
+                best = fmaxf(best, fmaxf(fabsf(yl), fabsf(yr)));
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(kFull, best, d));
+    if ((threadIdx.x & 31) == 0 && best > 0.0f) atomicMax(tp_bits + job.track, __float_as_uint(best));
 }
 
 }  // namespace ame

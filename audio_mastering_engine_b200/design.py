@@ -235,5 +235,20 @@ def track_params(settings, fs, n_frames, offset_frames=0, chunk_seconds=30, lut_
     _set_bq(p.kw[1], rb, ra)
     p.warm_kw = kw_warm_frames(fs)
     p.warm_eq = eq_warm_frames(fs, float(bass), float(mid_cut), float(presence), float(treble))
+    if settings.get("limiter"):                            # ffmpeg alimiter=level_in=1:level_out=1:limit=0.98:attack=5:release=50 (:223)
+        flags |= L.AME_F_LIMITER
+        limit = float(settings.get("limiter_limit", 0.98))
+        attack, release = float(settings.get("limiter_attack", 5.0)) / 1000.0, float(settings.get("limiter_release", 50.0)) / 1000.0
+        buffer_size = int(fs * attack * 2)                 # af_alimiter.c config_input, two channels
+        buffer_size -= buffer_size % 2
+        p.lim_frames = buffer_size // 2
+        p.lim_limit, p.lim_level, p.lim_fs_release = limit, 1.0 / limit, fs * release
+        p.lim_release_frames = int(math.ceil(fs * release))
+        thr = int(math.floor(limit * 32768.0))
+        while thr / 32768.0 <= limit:                      # smallest |s16| with x / 32768 > limit
+            thr += 1
+        p.lim_thr_i = thr
+    if settings.get("true_peak"):
+        flags |= L.AME_F_TRUE_PEAK
     p.flags = flags
     return p

@@ -114,9 +114,11 @@ class MasterPlan:
             d = dict(input_i=r.input_i, measured_i_2dp=r.measured_i_2dp, gain=r.gain,
                      rel_threshold_energy=r.rel_threshold, n_blocks=int(r.n_blocks),
                      normalized=bool(r.normalized), sample_peak=int(r.sample_peak),
-                     input_lra=r.input_lra, input_thresh=r.input_thresh)
-            # native-rate sample peak stands in for ffmpeg's 192 kHz-resampled peak (deviation D4)
-            d["input_tp"] = 20.0 * math.log10(r.sample_peak / 32768.0) if r.sample_peak > 0 else -math.inf
+                     input_lra=r.input_lra, input_thresh=r.input_thresh, true_peak=r.true_peak,
+                     true_peak_measured=bool(s.get("true_peak")))
+            # ffmpeg reports the sample peak of the stream resampled to 192 kHz; this is the BS.1770 Annex 2 4x
+            # oversampled peak when settings["true_peak"] is set, else the native-rate sample peak (deviation D4)
+            d["input_tp"] = 20.0 * math.log10(r.true_peak) if r.true_peak > 0 else -math.inf
             if r.normalized:
                 offset = float(s.get("lufs")) - r.measured_i_2dp
                 d["target_offset"] = offset
@@ -345,8 +347,11 @@ def write_wav(path, pcm, fs):
 
 
 def process_audio_with_ffmpeg_pipeline(settings, status_callback, progress_callback):
-    """Drop-in for audio_mastering_engine.py:171-226 (same callback sequence, same ValueError).
-    The final ffmpeg ``alimiter`` (:223) is not part of this build (out of scope D5)."""
+    """Drop-in for audio_mastering_engine.py:171-226 (same callback sequence, same ValueError): split -> per-chunk
+    chain -> concat -> two-pass loudness normalisation -> alimiter -> WAV.  The whole file is mastered by ONE call,
+    so the per-chunk status lines (the reference emits each when the chunk STARTS, :186-187) are emitted before it.
+    ffmpeg's loudnorm leaves linear mode (static gain) when measured_TP + offset > -1.5 dBTP or LRA > 11; this build
+    always applies the static gain (deviation D3) and says so through status_callback and the log."""
     input_file, output_file = settings.get("input_file"), settings.get("output_file")
     if not input_file or not output_file:
         raise ValueError("Input or output file not specified.")
@@ -357,14 +362,17 @@ def process_audio_with_ffmpeg_pipeline(settings, status_callback, progress_callb
     num_chunks = max(1, math.ceil(pcm.shape[0] / chunk_frames))
     total_steps = num_chunks + 4
     status_callback("Splitting complete.")
-    try:
-        out, info = master(pcm, fs, settings)
-    except Exception:
-        logging.exception("CRITICAL: Failed during processing.")
-        raise
+    run = dict(settings)
+    run.setdefault("limiter", True)                       # the reference always ends with alimiter (:223)
+    run.setdefault("true_peak", True)                     # needed to tell whether ffmpeg would have stayed in linear mode
     for i in range(num_chunks):
         status_callback(f"Processing chunk {i+1} of {num_chunks}...")
         progress_callback(i + 1, total_steps)
+    try:
+        out, info = master(pcm, fs, run)
+    except Exception:
+        logging.exception("CRITICAL: Failed during processing.")
+        raise
     status_callback("Re-assembling processed chunks with concat filter...")
     progress_callback(num_chunks + 1, total_steps)
     status_callback("Concatenation complete.")
@@ -373,6 +381,12 @@ def process_audio_with_ffmpeg_pipeline(settings, status_callback, progress_callb
         progress_callback(num_chunks + 2, total_steps)
         if not info["normalized"]:
             log.warning("Measured loudness is -inf (silent audio). Skipping normalization.")
+        elif not info.get("linear_mode_ok", True):
+            msg = (f"Note: input true peak {info['input_tp']:.2f} dBTP + offset {info['target_offset']:.2f} dB / LRA "
+                   f"{info['input_lra']:.1f} LU: ffmpeg loudnorm would switch to dynamic mode here; the static gain "
+                   f"{20 * math.log10(info['gain']):+.2f} dB was applied and the limiter catches the overshoot.")
+            log.warning(msg)
+            status_callback(msg)
     status_callback("Applying final limiting and exporting...")
     progress_callback(num_chunks + 3, total_steps)
     write_wav(output_file, out, fs)

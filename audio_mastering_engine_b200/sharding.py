@@ -130,28 +130,62 @@ class TimeShard:
             self.plan = None
 
 
+def _exchange_tail(sh, spans, group):
+    """Halo hand-off between neighbours: every rank sends the tail of its pre-normalisation signal (a few 100 ms of
+    audio) to the next rank and receives its predecessor's.  A rank without a span forwards what it received, so the
+    next non-empty rank still gets the tail of the nearest non-empty rank before it.  One stereo frame travels as one
+    int32 (NCCL has no int16)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    torch_dev = sh.dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    prev = None
+    if rank > 0:
+        prev = torch.empty((sh.send, 1), dtype=torch.int32, device=torch_dev)
+        dist.recv(prev, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
+    if rank < world - 1:
+        mine = sh.tail().view(torch.int32) if sh.n else prev
+        if mine is None:                                  # rank 0 without a span: nothing precedes the track
+            mine = torch.zeros((sh.send, 1), dtype=torch.int32, device=sh.dev)
+        dist.send(mine.to(torch_dev).contiguous(), dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1,
+                  group=group)
+    if sh.halo and prev is not None:
+        sh.set_halo(prev.to(sh.dev).view(torch.int16))
+    return int(sh.send) * 4 * ((rank > 0) + (rank < world - 1))
+
+
+def time_sharded_step(sh, spans, group=None):
+    """One pass of the by-time path over an already loaded TimeShard: pre-normalisation chain on the rank's span,
+    neighbour halo hand-off, local 400 ms block histogram, ONE all-reduce(sum) of the int64[1000] histogram, gain.
+    Returns (device int16[n,2] view, info, bytes this rank sent + received)."""
+    import torch
+    import torch.distributed as dist
+    sh.pre_normalisation()
+    moved = _exchange_tail(sh, spans, group)
+    hist = sh.histogram()
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)  # the one collective the math needs
+    else:
+        h = hist.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        hist.copy_(h)
+    out, info = sh.normalise(hist)
+    return out, info, moved + 2 * hist.numel() * 8
+
+
 def master_time_sharded(track, fs, settings, group=None, device=None, chunk_seconds=30, **plan_opts):
-    """Master ONE long track across the ranks of `group` (torch.distributed, NCCL).  Every rank passes the
-    same host track (or at least its own span); returns this rank's (span_begin, int16[n,2] numpy, info)."""
+    """Master ONE long track across the ranks of `group` (torch.distributed; NCCL on GPUs, gloo moves the two small
+    messages through the host).  Every rank passes the same track (numpy or tensor; at least its own span must be
+    valid); returns this rank's (span_begin, int16[n,2] numpy, info)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     device = torch.cuda.current_device() if device is None else device
     spans = plan_time_shards(len(track), fs, world, chunk_seconds)
     sh = TimeShard(spans[rank], fs, settings, rank, world, device, chunk_seconds, **plan_opts)
-    sh.load(np.ascontiguousarray(track[spans[rank][0]:spans[rank][1]]))
-    sh.pre_normalisation()
-    # halo hand-off: every rank publishes the tail of its pre-normalisation signal (a few 100 ms of audio) and
-    # takes the one of the nearest non-empty rank before it
-    tail = sh.tail().view(torch.int32)                   # one stereo frame = one int32 (NCCL has no int16)
-    tails = [torch.empty_like(tail) for _ in range(world)]
-    dist.all_gather(tails, tail, group=group)
-    if sh.halo:
-        prev = max(r for r in range(rank) if spans[r][1] > spans[r][0])
-        sh.set_halo(tails[prev].view(torch.int16))
-    hist = sh.histogram()
-    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)      # the one collective the math needs
-    out, info = sh.normalise(hist)
+    span = track[spans[rank][0]:spans[rank][1]]
+    sh.load(span if hasattr(span, "device") else np.ascontiguousarray(span))
+    out, info, _ = time_sharded_step(sh, spans, group)
     res = out.cpu().numpy()
     sh.close()
     return spans[rank][0], res, info

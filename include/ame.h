@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define AME_ABI_VERSION 5
-#define AME_N_KERNELS 10   /* kernels of the path, in launch order (ame_kernel_name) */
+#define AME_N_KERNELS 12   /* timed kernel slots of the path, in launch order (ame_kernel_name) */
 
 typedef enum {
     AME_OK = 0,
@@ -46,6 +46,8 @@ typedef enum {
 #define AME_F_WIDTH     2u  /* width != 1.0                    (:195) */
 #define AME_F_MULTIBAND 4u  /* settings["multiband"] truthy    (:197) */
 #define AME_F_NORMALIZE 8u  /* settings["lufs"] is not None    (:216) */
+#define AME_F_LIMITER   16u /* the final ffmpeg alimiter       (:223); not for time shards (global sequential state) */
+#define AME_F_TRUE_PEAK 32u /* also measure the BS.1770 Annex 2 true peak of the pre-normalisation signal */
 
 /* EQ stage kinds (apply_shelf_filter :283-289, apply_peak_filter :290-298) */
 #define AME_EQ_BYPASS      0  /* gain == 0: stage returns its input untouched */
@@ -102,7 +104,12 @@ typedef struct {
     double target_lufs;
     /* warm-up (frames processed before a tile only to converge filter state) */
     int32_t warm_eq, warm_xover, warm_kw;
-    int32_t pad1_;
+    /* ffmpeg alimiter (:223): limit, 1 / limit (auto level), sample_rate * release[s], look-ahead frames
+     * B = int(fs * attack[s] * 2) / 2, release in frames (rounded up), and the smallest |s16| whose x / 32768 exceeds
+     * the limit */
+    int32_t lim_frames;
+    double lim_limit, lim_level, lim_fs_release;
+    int32_t lim_release_frames, lim_thr_i;
 } ame_track_params;
 
 /* Per-track result of the loudness stage (the numbers ffmpeg prints as JSON at :229-237). */
@@ -116,6 +123,8 @@ typedef struct {
     int32_t sample_peak;     /* max |s16| of the pre-normalisation signal */
     double input_lra;        /* loudness range, LU (ebur128 short-term histogram, 10th..95th percentile) */
     double input_thresh;     /* relative gate threshold, LUFS (ffmpeg's input_thresh) */
+    double true_peak;        /* BS.1770 Annex 2 true peak of the pre-normalisation signal, linear (1.0 = full scale);
+                                the sample peak / 32768 when AME_F_TRUE_PEAK is not set or fs >= 192 kHz */
 } ame_track_result;
 
 typedef struct {

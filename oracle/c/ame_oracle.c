@@ -106,3 +106,96 @@ int ame_oracle_kfilter_df2(const int16_t *in, double *out, int64_t n_frames, con
     }
     return 0;
 }
+
+/* ame_oracle_alimiter() restates FFmpeg libavfilter/af_alimiter.c filter_frame() as the reference calls it at
+ * audio_mastering_engine.py:223 (level_in = level_out = 1, auto level on, asc off, latency off) together with the
+ * s16 -> dbl (x / 32768) and dbl -> s16 (clip(lrint(y * 32768))) conversions ffmpeg inserts around it.
+ * Must stay bit-identical to oracle/limiter.py alimiter_py (tests/test_oracle_limiter.py). */
+int ame_oracle_alimiter(const int16_t *in, int16_t *out, int64_t n_frames, double fs, double limit,
+                        double attack_ms, double release_ms, double *att_out) {
+    const int channels = 2;
+    const double attack = attack_ms / 1000.0, release = release_ms / 1000.0;
+    int buffer_size = (int)(fs * attack * channels);
+    buffer_size -= buffer_size % channels;
+    if (buffer_size < channels) return -1;
+    double *buffer = (double *)calloc((size_t)buffer_size, sizeof(double));
+    double *nextdelta = (double *)calloc((size_t)buffer_size, sizeof(double));
+    int *nextpos = (int *)malloc((size_t)buffer_size * sizeof(int));
+    if (!buffer || !nextdelta || !nextpos) { free(buffer); free(nextdelta); free(nextpos); return -2; }
+    for (int i = 0; i < buffer_size; ++i) nextpos[i] = -1;
+    double att = 1.0, delta = 0.0;
+    int pos = 0, nextiter = 0, nextlen = 0;
+    const double level = 1.0 / limit, level_out = 1.0, level_in = 1.0;
+    for (int64_t n = 0; n < n_frames; ++n) {
+        double peak = 0;
+        for (int c = 0; c < channels; ++c) {
+            double sample = ((double)in[n * channels + c] * (1.0 / 32768.0)) * level_in;
+            buffer[pos + c] = sample;
+            if (fabs(sample) > peak) peak = fabs(sample);
+        }
+        if (peak > limit) {
+            double patt = limit / peak < 1. ? limit / peak : 1.;
+            double rdelta = (1.0 - patt) / (fs * release);
+            double d = (limit / peak - att) / buffer_size * channels;
+            int found = 0, i;
+            if (d < delta) {
+                delta = d;
+                nextpos[0] = pos;
+                nextpos[1 % buffer_size] = -1;
+                nextdelta[0] = rdelta;
+                nextlen = 1;
+                nextiter = 0;
+            } else {
+                for (i = nextiter; i < nextiter + nextlen; i++) {
+                    int j = i % buffer_size;
+                    double ppeak = 0, pdelta;
+                    for (int c = 0; c < channels; c++)
+                        if (fabs(buffer[nextpos[j] + c]) > ppeak) ppeak = fabs(buffer[nextpos[j] + c]);
+                    pdelta = (limit / peak - limit / ppeak) / (((buffer_size - nextpos[j] + pos) % buffer_size) / channels);
+                    if (pdelta < nextdelta[j]) {
+                        nextdelta[j] = pdelta;
+                        found = 1;
+                        break;
+                    }
+                }
+                if (found) {
+                    nextlen = i - nextiter + 1;
+                    nextpos[(nextiter + nextlen) % buffer_size] = pos;
+                    nextdelta[(nextiter + nextlen) % buffer_size] = rdelta;
+                    nextpos[(nextiter + nextlen + 1) % buffer_size] = -1;
+                    nextlen++;
+                }
+            }
+        }
+        const int b0 = (pos + channels) % buffer_size;
+        peak = 0;
+        for (int c = 0; c < channels; c++)
+            if (fabs(buffer[b0 + c]) > peak) peak = fabs(buffer[b0 + c]);
+        att += delta;
+        double o[2];
+        for (int c = 0; c < channels; c++) o[c] = buffer[b0 + c] * att;
+        if (b0 == nextpos[nextiter]) {
+            delta = nextdelta[nextiter];
+            att = limit / peak;
+            nextlen -= 1;
+            nextpos[nextiter] = -1;
+            nextiter = (nextiter + 1) % buffer_size;
+        }
+        if (att > 1.) { att = 1.; delta = 0.; nextiter = 0; nextlen = 0; nextpos[0] = -1; }
+        if (att <= 0.) { att = 0.0000000000001; delta = (1.0 - att) / (fs * release); }
+        if (att != 1. && (1. - att) < 0.0000000000001) att = 1.;
+        if (delta != 0. && fabs(delta) < 0.00000000000001) delta = 0.;
+        for (int c = 0; c < channels; c++) {
+            double v = o[c];
+            if (v < -limit) v = -limit; else if (v > limit) v = limit;
+            v = v * level * level_out;
+            double r = rint(v * 32768.0);
+            if (r > 32767.0) r = 32767.0; else if (r < -32768.0) r = -32768.0;
+            out[n * channels + c] = (int16_t)r;
+        }
+        if (att_out) att_out[n] = att;
+        pos = (pos + channels) % buffer_size;
+    }
+    free(buffer); free(nextdelta); free(nextpos);
+    return 0;
+}

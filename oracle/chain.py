@@ -24,7 +24,8 @@ What is restated, and from where (all ``file:line`` are into the upstream refere
 Declared deviations: D1 chunk length is a parameter (default 30*fs frames) instead
 of ffmpeg's packet-granular cut; D2 pydub overlay's whole-millisecond slicing is not reproduced;
 D3 loudnorm *dynamic* mode is not reproduced (static gain always); D4 loudness is measured at the
-native rate, not ffmpeg's 192 kHz resampled stream; D5 the final ``alimiter`` (:223) is excluded.
+native rate, not ffmpeg's 192 kHz resampled stream, and the true peak is the BS.1770 Annex 2 meter;
+the final ``alimiter`` (:223) is restated in oracle/limiter.py and applied when settings["limiter"] is set.
 """
 from __future__ import annotations
 
@@ -464,6 +465,37 @@ def loudness_range_from_histogram(hist):
     return (10.0 * math.log10(h_en) - 0.691) - (10.0 * math.log10(l_en) - 0.691)
 
 
+# ITU-R BS.1770-4 Annex 2: 4-phase x 12-tap interpolating FIR of the true-peak meter (the coefficient table of the
+# recommendation).  y[4n + p] = sum_k h_p[k] x[n - k].
+TRUE_PEAK_FIR = np.array([
+    [0.0017089843750, 0.0109863281250, -0.0196533203125, 0.0332031250000, -0.0594482421875, 0.1373291015625,
+     0.9721679687500, -0.1022949218750, 0.0476074218750, -0.0266113281250, 0.0148925781250, -0.0083007812500],
+    [-0.0291748046875, 0.0292968750000, -0.0517578125000, 0.0891113281250, -0.1665039062500, 0.4650878906250,
+     0.7797851562500, -0.2003173828125, 0.1015625000000, -0.0582275390625, 0.0330810546875, -0.0189208984375],
+    [-0.0189208984375, 0.0330810546875, -0.0582275390625, 0.1015625000000, -0.2003173828125, 0.7797851562500,
+     0.4650878906250, -0.1665039062500, 0.0891113281250, -0.0517578125000, 0.0292968750000, -0.0291748046875],
+    [-0.0083007812500, 0.0148925781250, -0.0266113281250, 0.0476074218750, -0.1022949218750, 0.9721679687500,
+     0.1373291015625, -0.0594482421875, 0.0332031250000, -0.0196533203125, 0.0109863281250, 0.0017089843750]])
+
+
+def true_peak(pcm, fs):
+    """BS.1770-4 Annex 2 true peak (linear, 1.0 = full scale): 4x oversampling below 96 kHz, 2x (phases 0 and 2) below
+    192 kHz, the sample peak from there on.  NOT what ffmpeg's loudnorm prints as input_tp - that is the sample peak
+    of the stream swresample'd to 192 kHz (deviation D4); both estimate the same inter-sample peak."""
+    x = np.asarray(pcm, dtype=np.int16).astype(np.float64) * (1.0 / 32768.0)
+    if x.shape[0] == 0:
+        return 0.0
+    if fs >= 192000:
+        return float(np.abs(x).max())
+    phases = (0, 1, 2, 3) if fs < 96000 else (0, 2)
+    best = 0.0
+    for c in range(x.shape[1]):
+        for p in phases:
+            y = np.convolve(x[:, c], TRUE_PEAK_FIR[p])[: x.shape[0]]
+            best = max(best, float(np.abs(y).max()))
+    return best
+
+
 def integrated_loudness(pcm, fs):
     blocks, _ = gating_block_energies(pcm, fs)
     return gated_loudness_from_histogram(block_histogram(blocks))[0]
@@ -526,4 +558,10 @@ def master(pcm, fs, settings, chunk_seconds=30, taps=None, compress=None):
         out = normalize(pre, fs, settings.get("lufs"), info)
     else:
         out = pre
+    if settings.get("true_peak"):
+        info["true_peak"] = true_peak(pre, fs)
+    if settings.get("limiter"):                            # engine.py:223, after the (optional) normalisation
+        from . import limiter
+        out = limiter.alimiter(out, fs, settings.get("limiter_limit", 0.98), settings.get("limiter_attack", 5.0),
+                               settings.get("limiter_release", 50.0))
     return out, info

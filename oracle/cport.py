@@ -40,6 +40,9 @@ def _load():
         lib.ame_oracle_window_rms.restype = ctypes.c_int
         lib.ame_oracle_kfilter_df2.argtypes = [i16p, dp, ctypes.c_int64, dp, dp]
         lib.ame_oracle_kfilter_df2.restype = ctypes.c_int
+        lib.ame_oracle_alimiter.argtypes = [i16p, i16p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_double, dp]
+        lib.ame_oracle_alimiter.restype = ctypes.c_int
         _lib = lib
     return _lib
 
@@ -80,3 +83,18 @@ def kfilter_df2(pcm, b, a):
     lib.ame_oracle_kfilter_df2(pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), out.ctypes.data_as(dp),
                                pcm.shape[0], b.ctypes.data_as(dp), a.ctypes.data_as(dp))
     return out
+
+
+def alimiter(pcm, fs, limit=0.98, attack_ms=5.0, release_ms=50.0, return_att=False):
+    lib = _load()
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    out = np.empty_like(pcm)
+    n = pcm.shape[0]
+    att = np.empty(n, dtype=np.float64) if return_att else None
+    rc = lib.ame_oracle_alimiter(pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)),
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), n, float(fs), float(limit),
+                                 float(attack_ms), float(release_ms),
+                                 att.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if return_att else None)
+    if rc:
+        raise ValueError("alimiter: attack too short for this sample rate")
+    return (out, att) if return_att else out

@@ -7,6 +7,7 @@ saturating overlay, gain rounding) are held to bit-exact; the float paths are ex
 too except for isolated +-1 LSB truncation flips (FP64 filters evaluated with FMA / another order).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -218,7 +219,7 @@ def test_wav_entry_point_roundtrip(torch_cuda, tmp_path):
     assert any(s.startswith("Success:") for s in status), status
     assert progress[0] == (0, 100) and progress[-1] == (5, 5) and art == [None]
     out, fs2 = read_wav(dst)
-    ref, _ = chain.master(x, fs, settings)
+    ref, _ = chain.master(x, fs, dict(settings, limiter=True))        # the entry point ends with the limiter (:223)
     assert fs2 == fs and _maxdiff(out, ref) <= NULL_LSB
     # failure protocol (audio_mastering_engine.py:131-137)
     status.clear(); progress.clear(); art.clear(); tags.clear()
@@ -361,3 +362,186 @@ def test_plan_memory_pool_reuse_and_release(torch_cuda):
     fresh = [master(x, fs, synth.c2_settings(), chunk_seconds=1)[0], master(y, fs, synth.c1_settings())[0]]
     for a, b, c in zip(first, again, fresh):
         assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: limiter, true peak, full-size BASELINE configs, the shipped by-time path over torch.distributed
+# ------------------------------------------------------------------------------------------------
+def _hot(x, gain):
+    return np.clip(np.rint(x.astype(np.float64) * gain), -32768, 32767).astype(np.int16)
+
+
+def test_limiter_stage_is_bit_exact(torch_cuda):
+    """ffmpeg alimiter (:223) on the GPU = the oracle's restatement, bit for bit, given the same normalised signal:
+    quiet input (elementwise tiles only), sparse over-limit peaks, heavy clipping (one sequential run per track) and a
+    multi-tile track whose over-limit passages start and end sequential runs at tile boundaries."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import limiter
+    fs = 48000
+    flat = dict(bass_boost=0.0, mid_cut=0.0, presence_boost=0.0, treble_boost=0.0, analog_character=0, width=1.0,
+                lufs=None, multiband=False)
+    long = synth.track(5.0, fs, track_id=31) // 2                      # 240000 frames = 8 limiter tiles, all below the limit
+    long[30000:30400] = _hot(long[30000:30400], 9.0)                   # a passage inside tile 0
+    long[65500:65600, 0] = 32767                                       # straddles the tile 1 / tile 2 boundary (65536)
+    long[131071] = [-32768, 32767]                                     # last frame of tile 3
+    long[200000:200003] = 32700                                        # tile 6
+    cases = [synth.track(1.0, fs, track_id=30) // 2,                   # nothing over the limit
+             _hot(synth.track(1.5, fs, track_id=32, am_hz=3.0), 4.0),  # sparse peaks
+             _hot(synth.track(2.0, fs, track_id=33, am_hz=2.0), 14.0), # clipped most of the time
+             long, long[:32768], long[:32769], long[:100]]
+    for k, x in enumerate(cases):
+        plain, _ = master(x, fs, flat)
+        got, _ = master(x, fs, dict(flat, limiter=True))
+        want = limiter.alimiter(plain, fs)
+        assert np.array_equal(got, want), (k, _maxdiff(got, want), int(np.argmax(np.any(got != want, axis=1))))
+    # other look-ahead / release lengths and sample rates, in one batch with tracks that have no limiter
+    xs = [_hot(synth.track(0.8, f, track_id=40 + i, am_hz=4.0), 6.0) for i, f in enumerate((44100, 96000, 22050, 48000))]
+    fss = [44100, 96000, 22050, 48000]
+    sets = [dict(flat, limiter=True), dict(flat, limiter=True, limiter_limit=0.9, limiter_attack=2.0, limiter_release=20.0),
+            dict(flat), dict(synth.c2_settings(), limiter=True)]
+    outs, _ = master(xs, fss, sets, chunk_seconds=0.5)
+    plains, _ = master(xs, fss, [dict(s, limiter=False) for s in sets], chunk_seconds=0.5)
+    for x, f, s, o, pl in zip(xs, fss, sets, outs, plains):
+        want = limiter.alimiter(pl, f, s.get("limiter_limit", 0.98), s.get("limiter_attack", 5.0), s.get("limiter_release", 50.0)) \
+            if s.get("limiter") else pl
+        assert np.array_equal(o, want), f
+
+
+def test_master_with_limiter_vs_oracle(torch_cuda):
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    fs = 48000
+    x = synth.track(4.0, fs, track_id=12, am_hz=2.0)
+    s = dict(synth.c2_settings(), lufs=-9.0, limiter=True, true_peak=True)     # +10 dB of make-up gain: the limiter works
+    out, info = master(x, fs, s, chunk_seconds=1)
+    ref, rinfo = chain.master(x, fs, s, chunk_seconds=1)
+    assert _lufs_close(info["input_i"], rinfo["input_i"])
+    assert _maxdiff(out, ref) <= NULL_LSB
+    assert info["true_peak"] == pytest.approx(rinfo["true_peak"], rel=2e-5)
+    assert info["input_tp"] == pytest.approx(20 * math.log10(rinfo["true_peak"]), abs=1e-3)
+    for f2 in (44100, 96000, 192000):                                          # 4x, 2x, none
+        y = synth.track(0.5, f2, track_id=13)
+        _, i2 = master(y, f2, dict(synth.c1_settings(), true_peak=True))
+        _, r2 = chain.master(y, f2, dict(synth.c1_settings(), true_peak=True))
+        assert i2["true_peak"] == pytest.approx(r2["true_peak"], rel=2e-5), f2
+
+
+def test_quiet_track_through_the_entry_point_says_dynamic_mode(torch_cuda, tmp_path):
+    """A track far below the target: ffmpeg's loudnorm would leave linear mode (measured_TP + offset > -1.5 dBTP).
+    The drop-in entry point applies the static gain, limits, and SAYS so (status line + log) - never silently."""
+    from audio_mastering_engine_b200 import process_audio_with_ffmpeg_pipeline, read_wav, write_wav, synth
+    from oracle import chain
+    fs = 44100
+    x = (synth.track(2.0, fs, 14).astype(np.int32) // 6).astype(np.int16)      # about -35 LUFS
+    src, dst = str(tmp_path / "quiet.wav"), str(tmp_path / "quiet_out.wav")
+    write_wav(src, x, fs)
+    settings = dict(synth.c1_settings(), lufs=-14.0, input_file=src, output_file=dst)
+    status = []
+    process_audio_with_ffmpeg_pipeline(settings, status.append, lambda a, b: None)
+    assert any("dynamic mode" in s for s in status), status
+    out, _ = read_wav(dst)
+    ref, rinfo = chain.master(x, fs, dict(settings, limiter=True, true_peak=True))
+    assert _maxdiff(out, ref) <= NULL_LSB
+    assert 20 * math.log10(rinfo["true_peak"]) + (-14.0 - rinfo["measured_i_2dp"]) > -1.5
+
+
+def test_c1_full_size(torch_cuda):
+    """BASELINE config C1 at full size: 30 s, 44.1 kHz, EQ + warmth + width + -14 LUFS."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    fs = 44100
+    x = synth.track(30.0, fs, track_id=0)
+    for s in (synth.c1_settings(), dict(synth.c1_settings(), bass_boost=0.0, mid_cut=0.0, presence_boost=0.0, treble_boost=0.0)):
+        out, info = master(x, fs, s)
+        ref, rinfo = chain.master(x, fs, s)
+        assert _lufs_close(info["input_i"], rinfo["input_i"]) and info["measured_i_2dp"] == rinfo["measured_i_2dp"]
+        assert _maxdiff(out, ref) <= NULL_LSB
+
+
+def test_c5_shaped_192k_both_compressor_extremes(torch_cuda):
+    """BASELINE config C5 shape (bursts, beds, exact-zero gaps, clicks) at 192 kHz, 60 s, thresh -40 / ratio 10 and
+    thresh 0 / ratio 1, three 30 s-chunk boundaries... (two chunks)."""
+    from audio_mastering_engine_b200 import master, synth
+    from oracle import chain
+    fs = 192000
+    x = synth.stress_track(60.0, fs, track_id=4)
+    for th, ra in ((-40.0, 10.0), (0.0, 1.0)):
+        s = dict(synth.ALL_BOOST_EQ, analog_character=25, width=1.2, lufs=-14.0, multiband=True,
+                 low_thresh=th, low_ratio=ra, mid_thresh=th, mid_ratio=ra, high_thresh=th, high_ratio=ra)
+        out, info = master(x, fs, s)
+        ref, rinfo = chain.master(x, fs, s)
+        assert abs(info["input_i"] - rinfo["input_i"]) <= LUFS_TOL
+        assert _maxdiff(out, ref) <= NULL_LSB, (th, ra, _maxdiff(out, ref))
+
+
+def test_c4_slice_one_batch(torch_cuda):
+    """BASELINE config C4, track ids 0-35 (every EQ preset x width x warmth x multiband combination of the sweep and
+    two loudness targets), 30 s each, ONE batch in three waves and two workspace slots, every track against the oracle."""
+    from audio_mastering_engine_b200 import master, synth, EQ_PRESETS
+    from oracle import chain
+    fs, secs = 48000, 30.0
+    ids = list(range(36))
+    tracks = [synth.track(secs, fs, track_id=t, am_hz=2.0) for t in ids]
+    sets = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
+    sets += []
+    outs, infos = master(tracks, fs, sets, n_waves=3, n_slots=2)
+    worst = 0
+    for t, x, s, out, info in zip(ids, tracks, sets, outs, infos):
+        ref, rinfo = chain.master(x, fs, s)
+        d = _maxdiff(out, ref)
+        worst = max(worst, d)
+        assert d <= NULL_LSB, (t, d)
+        assert _lufs_close(info["input_i"], rinfo["input_i"]), t
+        assert info["measured_i_2dp"] == rinfo["measured_i_2dp"], t
+    print("C4 slice worst LSB diff", worst)
+
+
+def _dist_worker(rank, world, port, backend, fs, seconds, chunk, out_dir):
+    import torch
+    import torch.distributed as dist
+    from audio_mastering_engine_b200 import sharding, synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    begin, out, info = sharding.master_time_sharded(x, fs, synth.c2_settings(), device=dev, chunk_seconds=chunk)
+    np.save(os.path.join(out_dir, f"out{rank}.npy"), out)
+    np.save(os.path.join(out_dir, f"meta{rank}.npy"), np.array([begin, info["input_i"] if info else np.nan, info["n_blocks"] if info else -1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_dist(tmp_path, backend, world, fs=48000, seconds=7.0, chunk=1.0):
+    import socket
+    import torch.multiprocessing as mp
+    from audio_mastering_engine_b200 import master, synth
+    sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
+    mp.spawn(_dist_worker, args=(world, port, backend, fs, seconds, chunk, str(tmp_path)), nprocs=world, join=True)
+    x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    one, info1 = master(x, fs, synth.c2_settings(), chunk_seconds=chunk)
+    parts = [np.load(tmp_path / f"out{r}.npy") for r in range(world)]
+    metas = [np.load(tmp_path / f"meta{r}.npy") for r in range(world)]
+    assert [int(m[0]) for m in metas] == list(np.cumsum([0] + [len(p) for p in parts[:-1]]))
+    assert np.array_equal(np.concatenate(parts, axis=0), one)
+    for m in metas:
+        if m[2] >= 0:
+            assert m[1] == pytest.approx(info1["input_i"], abs=1e-9) and int(m[2]) == info1["n_blocks"]
+
+
+def test_shipped_time_sharded_path_two_processes_gloo(torch_cuda, tmp_path):
+    """sharding.master_time_sharded - the function bench.py and INTEGRATION.md use - run by TWO processes that share
+    this GPU, the halo hand-off and the histogram all-reduce going through torch.distributed (gloo): the concatenated
+    spans must equal the single-plan result bit for bit.  (No kernel waits on another process's kernel.)"""
+    _run_dist(tmp_path, "gloo", 2)
+    _run_dist(tmp_path, "gloo", 3, fs=44100, seconds=4.0)          # an empty-span-free ragged split
+
+
+def test_shipped_time_sharded_path_nccl(torch_cuda, tmp_path):
+    """The same over NCCL, one process per GPU (skipped on a one-GPU box; bench.py --gpus N times it as time_sharded)."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_dist(tmp_path, "nccl", 2)
