@@ -85,6 +85,8 @@ SYMBOLS = {
     "ame_master_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     "ame_measure_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_normalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult), C.c_void_p]),
+    "ame_shard_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    "ame_hist_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_stage_eq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_stage_band_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_stage_compress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1156,6 +1157,85 @@ int ame_normalize_device(ame_plan *p, const int64_t *d_hist, int16_t *d_out, ame
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
+    return AME_OK;
+}
+
+// ---- by-time sharding without Python: the two messages of the path over NCCL -------------------------------------
+// libame does not link NCCL: the entry points are resolved at run time from the libnccl the host process already
+// uses (dlopen with RTLD_NOLOAD first), so the library still loads where there is no NCCL at all.
+namespace {
+typedef int (*nccl_allreduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_sendrecv_t)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_group_t)(void);
+typedef const char *(*nccl_errstr_t)(int);
+struct NcclApi {
+    nccl_allreduce_t all_reduce = nullptr;
+    nccl_sendrecv_t send = nullptr, recv = nullptr;
+    nccl_group_t group_start = nullptr, group_end = nullptr;
+    nccl_errstr_t err = nullptr;
+    bool tried = false, ok = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+constexpr int kNcclInt8 = 0, kNcclInt64 = 4, kNcclSum = 0;     // ncclDataType_t / ncclRedOp_t values (nccl.h, stable since 2.0)
+
+const NcclApi *nccl_api() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (!g_nccl.tried) {
+        g_nccl.tried = true;
+        void *h = nullptr;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
+            if (!h) h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (h) {
+            g_nccl.all_reduce = (nccl_allreduce_t)dlsym(h, "ncclAllReduce");
+            g_nccl.send = (nccl_sendrecv_t)dlsym(h, "ncclSend");
+            g_nccl.recv = (nccl_sendrecv_t)dlsym(h, "ncclRecv");
+            g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
+            g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
+            g_nccl.err = (nccl_errstr_t)dlsym(h, "ncclGetErrorString");
+            g_nccl.ok = g_nccl.all_reduce && g_nccl.send && g_nccl.recv && g_nccl.group_start && g_nccl.group_end;
+        }
+    }
+    return g_nccl.ok ? &g_nccl : nullptr;
+}
+#define NCCL(api, call)                                                                            \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0) return fail(AME_E_CUDA, "%s failed: %s", #call, (api)->err ? (api)->err(r_) : "NCCL error"); \
+    } while (0)
+}  // namespace
+
+int ame_hist_allreduce(ame_plan *p, int64_t *d_hist, void *nccl_comm, void *stream) {
+    if (!p || !d_hist || !nccl_comm) return fail(AME_E_INVALID, "NULL argument");
+    const NcclApi *api = nccl_api();
+    if (!api) return fail(AME_E_UNSUPPORTED, "libnccl.so.2 not found in this process");
+    GUARD(p->device);
+    NCCL(api, api->all_reduce(d_hist, d_hist, (size_t)p->n_tracks * 1000, kNcclInt64, kNcclSum, nccl_comm, (cudaStream_t)stream));
+    return AME_OK;
+}
+
+int ame_shard_halo_exchange(ame_plan *p, int16_t *d_pre, void *nccl_comm, int prev_rank, int next_rank, int64_t send_frames,
+                            void *stream) {
+    if (!p || !d_pre || !nccl_comm) return fail(AME_E_INVALID, "NULL argument");
+    if (p->n_tracks != 1) return fail(AME_E_INVALID, "a time shard is a plan over one track");
+    const ame_track_params &tp = p->tracks[0];
+    const int64_t have = tp.halo_frames + tp.n_frames;
+    if (next_rank >= 0 && (send_frames <= 0 || send_frames > have))
+        return fail(AME_E_UNSUPPORTED, "the shard holds %lld frames, fewer than the %lld the next shard's halo needs", (long long)have,
+                    (long long)send_frames);
+    const NcclApi *api = nccl_api();
+    if (!api) return fail(AME_E_UNSUPPORTED, "libnccl.so.2 not found in this process");
+    GUARD(p->device);
+    int16_t *base = d_pre + 2 * tp.offset_frames;
+    NCCL(api, api->group_start());
+    if (next_rank >= 0)
+        NCCL(api, api->send(base + 2 * (have - send_frames), (size_t)send_frames * 4, kNcclInt8, next_rank, nccl_comm, (cudaStream_t)stream));
+    if (prev_rank >= 0 && tp.halo_frames > 0)
+        NCCL(api, api->recv(base, (size_t)tp.halo_frames * 4, kNcclInt8, prev_rank, nccl_comm, (cudaStream_t)stream));
+    NCCL(api, api->group_end());
     return AME_OK;
 }
 

@@ -208,6 +208,16 @@ int ame_measure_device(ame_plan *plan, const int16_t *d_in, int64_t *d_hist, voi
 int ame_normalize_device(ame_plan *plan, const int64_t *d_hist, int16_t *d_out,
                          ame_track_result *results, void *stream);
 
+/* by-time sharding from a host that is not Python: one plan over ONE track [halo | span] per
+ * rank; between ame_stage_compress and ame_stage_loudness_hist a rank sends the last send_frames of its
+ * pre-normalisation signal to the next rank and receives its own halo from the previous one (rank < 0 = none), and
+ * between ame_stage_loudness_hist and ame_stage_apply_gain the int64[n_tracks][1000] histograms are all-reduced (sum)
+ * so that every rank derives the same integrated loudness and gain.  nccl_comm is the caller's ncclComm_t; NCCL is
+ * resolved from the process at run time (AME_E_UNSUPPORTED when there is none).  examples/time_shard_nccl.c. */
+int ame_shard_halo_exchange(ame_plan *plan, int16_t *d_pre, void *nccl_comm, int prev_rank, int next_rank,
+                            int64_t send_frames, void *stream);
+int ame_hist_allreduce(ame_plan *plan, int64_t *d_hist, void *nccl_comm, void *stream);
+
 /* stage entry points (parity taps; each replaces the named reference function; plans with ONE wave) */
 /* warmth -> int16 -> EQ -> width -> int16: apply_analog_character, audio_segment_to_float_array,
  * apply_eq_to_samples, apply_stereo_width, float_array_to_audio_segment (:192-196) */

@@ -113,3 +113,12 @@ def test_warmup_length_bounds_state_error():
     cold = sosfilt(sos, x[w:])           # zero state at frame w
     err = np.abs(full[2 * w:] - cold[w:]).max() / np.sqrt(np.mean(full ** 2))
     assert err < 1e-12
+
+
+def test_c_example_of_the_by_time_path_compiles(tmp_path):
+    """examples/time_shard_nccl.c shows a non-Python host running one rank of the time-sharded path on include/ame.h
+    alone (ame_shard_halo_exchange + ame_hist_allreduce): it must keep compiling against the header."""
+    import subprocess
+    src = os.path.join(ROOT, "examples", "time_shard_nccl.c")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", src,
+                           "-o", str(tmp_path / "ts.o")])

@@ -545,3 +545,80 @@ def test_shipped_time_sharded_path_nccl(torch_cuda, tmp_path):
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run_dist(tmp_path, "nccl", 2)
+
+
+def _c_abi_shard_worker(rank, world, fs, seconds, chunk, out_dir):
+    """One rank of examples/time_shard_nccl.c, driven through ctypes: its own ncclComm_t (created with libnccl's C API,
+    no torch.distributed), ame_shard_halo_exchange + ame_hist_allreduce from libame."""
+    import ctypes as C
+    import glob
+    import time
+    import torch
+    from audio_mastering_engine_b200 import MasterPlan, sharding, synth
+    from audio_mastering_engine_b200 import _lib as L
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
+    nccl = C.CDLL(cands[0] if cands else "libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+    uid = UniqueId()
+    path = os.path.join(out_dir, "nccl_id.bin")
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+        with open(path + ".tmp", "wb") as fh:
+            fh.write(bytes(uid))
+        os.rename(path + ".tmp", path)
+    else:
+        for _ in range(600):
+            if os.path.exists(path):
+                break
+            time.sleep(0.05)
+        C.memmove(C.byref(uid), open(path, "rb").read(), 128)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+
+    x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    spans = sharding.plan_time_shards(len(x), fs, world, chunk)
+    b, e = spans[rank]
+    halo = sharding.halo_frames(fs) if rank > 0 else 0
+    plan = MasterPlan([e - b], fs, synth.c2_settings(), device=rank, chunk_seconds=chunk, halos=[halo])
+    tf = plan.total_frames
+    d_in = torch.zeros((tf, 2), dtype=torch.int16, device=dev)
+    d_in[halo:halo + e - b] = torch.from_numpy(np.ascontiguousarray(x[b:e])).to(dev)
+    d_pre, d_out = torch.zeros_like(d_in), torch.zeros_like(d_in)
+    d_bands = torch.zeros((3, max(plan.mb_frames, 1), 2), dtype=torch.int16, device=dev)
+    d_hist = torch.zeros((1, 1000), dtype=torch.int64, device=dev)
+    lib, h = plan.lib, plan.handle
+    plan.stage_eq(d_in, d_pre); plan.stage_band_split(d_pre, d_bands); plan.stage_compress(d_bands, d_pre)
+    L.check(lib.ame_shard_halo_exchange(h, C.c_void_p(d_pre.data_ptr()), comm, rank - 1 if rank > 0 else -1,
+                                        rank + 1 if rank + 1 < world else -1, sharding.halo_frames(fs), None))
+    plan.stage_loudness_hist(d_pre, d_hist)
+    L.check(lib.ame_hist_allreduce(h, C.c_void_p(d_hist.data_ptr()), comm, None))
+    info = plan.stage_apply_gain(d_pre, d_hist, d_out)[0]
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"out{rank}.npy"), d_out[halo:halo + e - b].cpu().numpy())
+    np.save(os.path.join(out_dir, f"meta{rank}.npy"), np.array([b, info["input_i"], info["n_blocks"]]))
+    plan.close()
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    nccl.ncclCommDestroy(comm)
+
+
+def test_c_abi_time_shard_entry_points_nccl(torch_cuda, tmp_path):
+    """ame_shard_halo_exchange + ame_hist_allreduce (the by-time path for a host that is not Python) on two GPUs with a
+    communicator made by libnccl's own C API: bit-identical to the single-plan result."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from audio_mastering_engine_b200 import master, synth
+    fs, seconds, chunk, world = 48000, 6.0, 1.0, 2
+    mp.spawn(_c_abi_shard_worker, args=(world, fs, seconds, chunk, str(tmp_path)), nprocs=world, join=True)
+    x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    one, info1 = master(x, fs, synth.c2_settings(), chunk_seconds=chunk)
+    parts = [np.load(tmp_path / f"out{r}.npy") for r in range(world)]
+    assert np.array_equal(np.concatenate(parts, axis=0), one)
+    for r in range(world):
+        m = np.load(tmp_path / f"meta{r}.npy")
+        assert m[1] == pytest.approx(info1["input_i"], abs=1e-9) and int(m[2]) == info1["n_blocks"]
