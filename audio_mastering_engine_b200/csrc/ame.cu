@@ -169,7 +169,8 @@ struct ame_plan {
     int slot_tiles = 0, slot_chains = 0;
     int64_t n_sb_total = 0;
     int eq_tile = 0, split_tile = 0, kw_tile_sb = 0;
-    int n_sm = 148, chain_warps = 0;      // see chain_threads()
+    int n_sm = 148, chain_warps = 0;      // see chain_lanes()
+    int precision = 0;                    // 1 = the FP32 EQ experiment
     size_t ws_bytes = 0;
     int64_t launches = 0;
     // device
@@ -434,7 +435,10 @@ Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) 
 int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cudaStream_t s) {
     if (!w.eq_n) return AME_OK;
     t_begin(p, S_EQ, s);
-    k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+    if (p->precision == 1)
+        k_eq_f32<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+    else
+        k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
     LAUNCH_CHECK(p);
     t_end(p, S_EQ, s);
     return AME_OK;
@@ -715,7 +719,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     p->n_sm = n_sm;
     p->chain_warps = std::max(-1, std::min(o.chain_warps, kChainMaxThreads / 32));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
+    p->precision = o.precision == 1 ? 1 : 0;
+    if (p->precision == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq_f32, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_eq, k_eq, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_split, k_band_split<true>, 128, 0);
     if (const char *e = std::getenv("AME_EQ_CTAS_PER_SM")) occ_eq = std::max(1, std::atoi(e));       // experiments
     if (const char *e = std::getenv("AME_SPLIT_CTAS_PER_SM")) occ_split = std::max(1, std::atoi(e));

@@ -93,18 +93,18 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return (uint32_t)(u
 // returns for the reference's shelves / band-passes / crossovers has this shape (validated on the host),
 // which saves two coefficient registers per section.  DF-II transposed as scipy evaluates it:
 //   y = b0 x + z0 ; z0 = (z1 + b1 x) - a1 y ; z1 = b2 x - a2 y        with b1 x = 2S (b0 x) exactly.
-template <int S>
-__device__ __forceinline__ double bw_step(double b0, double a1, double a2, double &z0, double &z1, double x) {
-    const double y = fma(b0, x, z0);
-    const double t = b0 * x;
-    z0 = fma(-a1, y, fma(2.0 * S, t, z1));
+template <int S, typename F>
+__device__ __forceinline__ F bw_step(F b0, F a1, F a2, F &z0, F &z1, F x) {
+    const F y = fma(b0, x, z0);
+    const F t = b0 * x;
+    z0 = fma(-a1, y, fma((F)(2.0 * S), t, z1));
     z1 = fma(-a2, y, t);
     return y;
 }
-template <int S>   // b0 == 1
-__device__ __forceinline__ double bw_step1(double a1, double a2, double &z0, double &z1, double x) {
-    const double y = x + z0;
-    z0 = fma(-a1, y, fma(2.0 * S, x, z1));
+template <int S, typename F>   // b0 == 1
+__device__ __forceinline__ F bw_step1(F a1, F a2, F &z0, F &z1, F x) {
+    const F y = x + z0;
+    z0 = fma(-a1, y, fma((F)(2.0 * S), x, z1));
     z1 = fma(-a2, y, x);
     return y;
 }
@@ -117,18 +117,26 @@ __device__ __forceinline__ double shelf_cut(double v, double f, double g) {
     const double t = FIRST ? (double)__fmul_rn((float)v, (float)g) : __dmul_rn(v, g);
     return __dadd_rn(t, __dsub_rn(f, t));
 }
-
-struct PeakCoef { double b0, a1[4], a2[4]; };     // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
-__device__ __forceinline__ void load_peak(PeakCoef &c, const ame_eq_stage &st) {
-    c.b0 = st.s[0].b0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { c.a1[i] = st.s[i].a1; c.a2[i] = st.s[i].a2; }
+template <bool FIRST>
+__device__ __forceinline__ float shelf_cut(float v, float f, float g) {          // the FP32 experiment (precision = 1)
+    const float t = __fmul_rn(v, g);
+    return __fadd_rn(t, __fsub_rn(f, t));
 }
-__device__ __forceinline__ double peak_step(const PeakCoef &c, double *z, double x) {
-    double t = bw_step<1>(c.b0, c.a1[0], c.a2[0], z[0], z[1], x);
-    t = bw_step1<1>(c.a1[1], c.a2[1], z[2], z[3], t);
-    t = bw_step1<-1>(c.a1[2], c.a2[2], z[4], z[5], t);
-    return bw_step1<-1>(c.a1[3], c.a2[3], z[6], z[7], t);
+
+template <typename F>
+struct PeakCoef { F b0, a1[4], a2[4]; };          // butter(4, bandpass, sos): signs (+,+,-,-), sections 1..3 unit gain
+template <typename F>
+__device__ __forceinline__ void load_peak(PeakCoef<F> &c, const ame_eq_stage &st) {
+    c.b0 = (F)st.s[0].b0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.a1[i] = (F)st.s[i].a1; c.a2[i] = (F)st.s[i].a2; }
+}
+template <typename F>
+__device__ __forceinline__ F peak_step(const PeakCoef<F> &c, F *z, F x) {
+    F t = bw_step<1, F>(c.b0, c.a1[0], c.a2[0], z[0], z[1], x);
+    t = bw_step1<1, F>(c.a1[1], c.a2[1], z[2], z[3], t);
+    t = bw_step1<-1, F>(c.a1[2], c.a2[2], z[4], z[5], t);
+    return bw_step1<-1, F>(c.a1[3], c.a2[3], z[6], z[7], t);
 }
 
 // exact int16 -> x / 32768 as double in ONE add: bits of 2^37 + (x + 2^31) * 2^-15, minus 2^37 + 2^16
@@ -141,8 +149,10 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 // ONE THREAD per tile, both channels: the L and R cascades are two independent dependency chains in one
 // instruction stream (the kernel is bound by FP64 latency, not by registers), and the cross-channel
 // stages (warmth, width, packing) need no shuffles.  MASK = active EQ stages, WARM = warmth on.
+// F = double is the product (what scipy computes, :272-298); F = float is the precision experiment of DESIGN.md
+// (ame_plan_options.precision = 1): the same cascade with float32 coefficients and state.
 // ------------------------------------------------------------------------------------------------
-template <int MASK, bool WARM>
+template <int MASK, bool WARM, typename F>
 __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
                                         const double *__restrict__ luts, const int16_t *__restrict__ in,
                                         int16_t *__restrict__ pre) {
@@ -154,22 +164,22 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         wl_b0 = tp->wl_b0; wl_b1 = tp->wl_b1; wl_a1 = tp->wl_a1; wl_gm1 = tp->wl_gm1;
         wh_b0 = tp->wh_b0; wh_b1 = tp->wh_b1; wh_a1 = tp->wh_a1; wh_gm1 = tp->wh_gm1;
     }
-    double s0_b0 = 0, s0_a1 = 0, s0_a2 = 0, g0 = 0, gm0 = 0, s3_b0 = 0, s3_a1 = 0, s3_a2 = 0, g3 = 0, gm3 = 0, gm1 = 0, gm2 = 0;
+    F s0_b0 = 0, s0_a1 = 0, s0_a2 = 0, g0 = 0, gm0 = 0, s3_b0 = 0, s3_a1 = 0, s3_a2 = 0, g3 = 0, gm3 = 0, gm1 = 0, gm2 = 0;
     bool boost0 = false, boost3 = false;
-    PeakCoef p1, p2;
+    PeakCoef<F> p1, p2;
     if (MASK & 1) {
-        s0_b0 = tp->eq[0].s[0].b0; s0_a1 = tp->eq[0].s[0].a1; s0_a2 = tp->eq[0].s[0].a2;
-        g0 = tp->eq[0].g; gm0 = tp->eq[0].gm1; boost0 = tp->eq[0].kind == AME_EQ_SHELF_BOOST;
+        s0_b0 = (F)tp->eq[0].s[0].b0; s0_a1 = (F)tp->eq[0].s[0].a1; s0_a2 = (F)tp->eq[0].s[0].a2;
+        g0 = (F)tp->eq[0].g; gm0 = (F)tp->eq[0].gm1; boost0 = tp->eq[0].kind == AME_EQ_SHELF_BOOST;
     }
-    if (MASK & 2) { load_peak(p1, tp->eq[1]); gm1 = tp->eq[1].gm1; }
-    if (MASK & 4) { load_peak(p2, tp->eq[2]); gm2 = tp->eq[2].gm1; }
+    if (MASK & 2) { load_peak(p1, tp->eq[1]); gm1 = (F)tp->eq[1].gm1; }
+    if (MASK & 4) { load_peak(p2, tp->eq[2]); gm2 = (F)tp->eq[2].gm1; }
     if (MASK & 8) {
-        s3_b0 = tp->eq[3].s[0].b0; s3_a1 = tp->eq[3].s[0].a1; s3_a2 = tp->eq[3].s[0].a2;
-        g3 = tp->eq[3].g; gm3 = tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
+        s3_b0 = (F)tp->eq[3].s[0].b0; s3_a1 = (F)tp->eq[3].s[0].a1; s3_a2 = (F)tp->eq[3].s[0].a2;
+        g3 = (F)tp->eq[3].g; gm3 = (F)tp->eq[3].gm1; boost3 = tp->eq[3].kind == AME_EQ_SHELF_BOOST;
     }
-    double zl[20], zr[20];
+    F zl[20], zr[20];
 #pragma unroll
-    for (int i = 0; i < 20; ++i) { zl[i] = 0.0; zr[i] = 0.0; }
+    for (int i = 0; i < 20; ++i) { zl[i] = 0; zr[i] = 0; }
 
     const int64_t warm = (MASK != 0) ? (int64_t)tp->warm_eq : 0;
     int64_t f_lo = job.tile_begin - warm;
@@ -179,18 +189,18 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     const int64_t g0f = f_lo & ~(int64_t)3;               // first 4-aligned group
     const int n_it = (int)((f_hi - g0f + 3) >> 2);
 
-    auto cascade = [&](double v, double *z) -> float {     // one channel through the 4 EQ stages
+    auto cascade = [&](F v, F *z) -> float {               // one channel through the 4 EQ stages
         if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
-            const double f = bw_step<1>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
+            const F f = bw_step<1, F>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
             v = boost0 ? v + (f - v) * gm0 : shelf_cut<true>(v, f, g0);
         }
         if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
         if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
         if (MASK & 8) {   // apply_shelf_filter 8 kHz high
-            const double f = bw_step<-1>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
+            const F f = bw_step<-1, F>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
             v = boost3 ? v + (f - v) * gm3 : shelf_cut<(MASK & 7) == 0>(v, f, g3);
         }
-        return __double2float_rn(v);                       // samples[:, i] = ... into the float32 array (:274)
+        return (float)v;                                   // samples[:, i] = ... into the float32 array (:274), round to nearest
     };
 
     // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
@@ -215,8 +225,8 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         // audio_segment_to_float_array (:250-253): x / 32768 is exact in float32 and in float64
         float yl, yr;
         if (MASK != 0) {
-            yl = cascade(i16_to_unit(xl), zl);
-            yr = cascade(i16_to_unit(xr), zr);
+            yl = cascade((F)i16_to_unit(xl), zl);
+            yr = cascade((F)i16_to_unit(xr), zr);
         } else {
             yl = __fmul_rn((float)xl, 1.0f / 32768.0f);
             yr = __fmul_rn((float)xr, 1.0f / 32768.0f);
@@ -271,23 +281,27 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     }
 }
 
-__global__ void __launch_bounds__(128, 2)
-k_eq(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
-     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    const TileJob job = jobs[j];
-    if (job.tile_end <= job.tile_begin) return;           // padding job (tracks get whole warps)
-    const ame_track_params *tp = tracks + job.track;
-    switch (job.variant) {      // bits 0-3: EQ stages, bit 4: warmth
-#define AME_EQ_CASE(M) case M: eq_tile<M, false>(job, tp, luts, in, pre); break; \
-                       case M + 16: eq_tile<M, true>(job, tp, luts, in, pre); break;
-        AME_EQ_CASE(0) AME_EQ_CASE(1) AME_EQ_CASE(2) AME_EQ_CASE(3) AME_EQ_CASE(4) AME_EQ_CASE(5)
-        AME_EQ_CASE(6) AME_EQ_CASE(7) AME_EQ_CASE(8) AME_EQ_CASE(9) AME_EQ_CASE(10) AME_EQ_CASE(11)
-        AME_EQ_CASE(12) AME_EQ_CASE(13) AME_EQ_CASE(14) AME_EQ_CASE(15)
-#undef AME_EQ_CASE
-    }
+#define AME_EQ_KERNEL(NAME, F)                                                                                     \
+__global__ void __launch_bounds__(128, 2)                                                                          \
+NAME(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,                    \
+     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {                 \
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;                                                           \
+    if (j >= n_jobs) return;                                                                                       \
+    const TileJob job = jobs[j];                                                                                   \
+    if (job.tile_end <= job.tile_begin) return;           /* padding job (tracks get whole warps) */               \
+    const ame_track_params *tp = tracks + job.track;                                                               \
+    switch (job.variant) {      /* bits 0-3: EQ stages, bit 4: warmth */                                           \
+        AME_EQ_CASE(0, F) AME_EQ_CASE(1, F) AME_EQ_CASE(2, F) AME_EQ_CASE(3, F) AME_EQ_CASE(4, F) AME_EQ_CASE(5, F) \
+        AME_EQ_CASE(6, F) AME_EQ_CASE(7, F) AME_EQ_CASE(8, F) AME_EQ_CASE(9, F) AME_EQ_CASE(10, F) AME_EQ_CASE(11, F) \
+        AME_EQ_CASE(12, F) AME_EQ_CASE(13, F) AME_EQ_CASE(14, F) AME_EQ_CASE(15, F)                                 \
+    }                                                                                                              \
 }
+#define AME_EQ_CASE(M, F) case M: eq_tile<M, false, F>(job, tp, luts, in, pre); break; \
+                          case M + 16: eq_tile<M, true, F>(job, tp, luts, in, pre); break;
+AME_EQ_KERNEL(k_eq, double)
+AME_EQ_KERNEL(k_eq_f32, float)      // precision experiment only (ame_plan_options.precision = 1)
+#undef AME_EQ_CASE
+#undef AME_EQ_KERNEL
 
 // ------------------------------------------------------------------------------------------------
 // k_band_split: int16 pre -> Butterworth-4 LP 250 / HP 4k in FP64, mid = x - low - high, each band
@@ -327,8 +341,8 @@ k_band_split(const __grid_constant__ XoverCfg xc, const TileJob *__restrict__ jo
 
     auto split = [&](int xm, double *z, int &p0, int &p1, int &p2) {
         const double x = i16_to_unit(xm);
-        const double lo = bw_step1<1>(la11, la21, z[2], z[3], bw_step<1>(lb0, la10, la20, z[0], z[1], x));
-        const double hi = bw_step1<-1>(ha11, ha21, z[6], z[7], bw_step<-1>(hb0, ha10, ha20, z[4], z[5], x));
+        const double lo = bw_step1<1, double>(la11, la21, z[2], z[3], bw_step<1, double>(lb0, la10, la20, z[0], z[1], x));
+        const double hi = bw_step1<-1, double>(ha11, ha21, z[6], z[7], bw_step<-1, double>(hb0, ha10, ha20, z[4], z[5], x));
         const double mid = __dsub_rn(__dsub_rn(x, lo), hi);
         p0 = to_pcm_f64(lo); p1 = to_pcm_f64(mid); p2 = to_pcm_f64(hi);
     };

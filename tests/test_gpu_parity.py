@@ -432,17 +432,17 @@ def test_quiet_track_through_the_entry_point_says_dynamic_mode(torch_cuda, tmp_p
     from audio_mastering_engine_b200 import process_audio_with_ffmpeg_pipeline, read_wav, write_wav, synth
     from oracle import chain
     fs = 44100
-    x = (synth.track(2.0, fs, 14).astype(np.int32) // 6).astype(np.int16)      # about -35 LUFS
+    x = (synth.stress_track(12.0, fs, 14).astype(np.int32) // 4).astype(np.int16)   # -24 LUFS, clicks 15 dB over the bursts
     src, dst = str(tmp_path / "quiet.wav"), str(tmp_path / "quiet_out.wav")
     write_wav(src, x, fs)
-    settings = dict(synth.c1_settings(), lufs=-14.0, input_file=src, output_file=dst)
+    settings = dict(synth.c1_settings(), lufs=-9.0, input_file=src, output_file=dst)
     status = []
     process_audio_with_ffmpeg_pipeline(settings, status.append, lambda a, b: None)
     assert any("dynamic mode" in s for s in status), status
     out, _ = read_wav(dst)
     ref, rinfo = chain.master(x, fs, dict(settings, limiter=True, true_peak=True))
     assert _maxdiff(out, ref) <= NULL_LSB
-    assert 20 * math.log10(rinfo["true_peak"]) + (-14.0 - rinfo["measured_i_2dp"]) > -1.5
+    assert 20 * math.log10(rinfo["true_peak"]) + (-9.0 - rinfo["measured_i_2dp"]) > -1.5
 
 
 def test_c1_full_size(torch_cuda):
