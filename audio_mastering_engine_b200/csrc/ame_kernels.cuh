@@ -152,7 +152,11 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 // F = double is the product (what scipy computes, :272-298); F = float is the precision experiment of DESIGN.md
 // (ame_plan_options.precision = 1): the same cascade with float32 coefficients and state.
 // ------------------------------------------------------------------------------------------------
-template <int MASK, bool WARM, typename F>
+// SKEW (experiment, not instantiated in the product): the four stages work on four consecutive frames at once - stage
+// s on frame i - s, handing its output to stage s + 1 through a register - so that one iteration holds 8 independent
+// dependency chains instead of 2.  Same bytes out; measured 11.00 ms against 11.07 ms for the plain order on the
+// 128-track launch (profiles/r02/summary.md): the compiler's schedule of the plain loop already overlaps the stages.
+template <int MASK, bool WARM, typename F, bool SKEW>
 __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
                                         const double *__restrict__ luts, const int16_t *__restrict__ in,
                                         int16_t *__restrict__ pre) {
@@ -189,19 +193,26 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     const int64_t g0f = f_lo & ~(int64_t)3;               // first 4-aligned group
     const int n_it = (int)((f_hi - g0f + 3) >> 2);
 
-    auto cascade = [&](F v, F *z) -> float {               // one channel through the 4 EQ stages
-        if (MASK & 1) {   // apply_shelf_filter 250 Hz low (:283-289)
+    auto st0 = [&](F v, F *z) -> F {   // apply_shelf_filter 250 Hz low (:283-289)
+        if (MASK & 1) {
             const F f = bw_step<1, F>(s0_b0, s0_a1, s0_a2, z[0], z[1], v);
             v = boost0 ? v + (f - v) * gm0 : shelf_cut<true>(v, f, g0);
         }
-        if (MASK & 2) v = v + peak_step(p1, z + 2, v) * gm1;    // apply_peak_filter 1 kHz (:290-298)
-        if (MASK & 4) v = v + peak_step(p2, z + 10, v) * gm2;   // apply_peak_filter 4 kHz
-        if (MASK & 8) {   // apply_shelf_filter 8 kHz high
+        return v;
+    };
+    auto st1 = [&](F v, F *z) -> F { return (MASK & 2) ? v + peak_step(p1, z + 2, v) * gm1 : v; };    // apply_peak_filter 1 kHz (:290-298)
+    auto st2 = [&](F v, F *z) -> F { return (MASK & 4) ? v + peak_step(p2, z + 10, v) * gm2 : v; };   // apply_peak_filter 4 kHz
+    auto st3 = [&](F v, F *z) -> F {   // apply_shelf_filter 8 kHz high
+        if (MASK & 8) {
             const F f = bw_step<-1, F>(s3_b0, s3_a1, s3_a2, z[18], z[19], v);
             v = boost3 ? v + (f - v) * gm3 : shelf_cut<(MASK & 7) == 0>(v, f, g3);
         }
-        return (float)v;                                   // samples[:, i] = ... into the float32 array (:274), round to nearest
+        return v;
     };
+    auto cascade = [&](F v, F *z) -> float {               // one channel through the 4 EQ stages
+        return (float)st3(st2(st1(st0(v, z), z), z), z);   // samples[:, i] = ... into the float32 array (:274), round to nearest
+    };
+    F q0l = 0, q0r = 0, q1l = 0, q1r = 0, q2l = 0, q2r = 0, q3l = 0, q3r = 0;     // SKEW: stage outputs of the last four frames
 
     // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
     auto frame = [&](uint32_t w, double lutL, double lutR) -> uint32_t {
@@ -224,7 +235,14 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         }
         // audio_segment_to_float_array (:250-253): x / 32768 is exact in float32 and in float64
         float yl, yr;
-        if (MASK != 0) {
+        if (SKEW && MASK != 0) {
+            yl = (float)q3l; yr = (float)q3r;              // the frame that entered four iterations ago leaves
+            const F o3l = st3(q2l, zl), o3r = st3(q2r, zr);
+            const F o2l = st2(q1l, zl), o2r = st2(q1r, zr);
+            const F o1l = st1(q0l, zl), o1r = st1(q0r, zr);
+            q0l = st0((F)i16_to_unit(xl), zl); q0r = st0((F)i16_to_unit(xr), zr);
+            q3l = o3l; q3r = o3r; q2l = o2l; q2r = o2r; q1l = o1l; q1r = o1r;
+        } else if (MASK != 0) {
             yl = cascade((F)i16_to_unit(xl), zl);
             yr = cascade((F)i16_to_unit(xr), zr);
         } else {
@@ -258,22 +276,24 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
         }
     };
     if (WARM) fetch_lut(cur, lutL, lutR);
-    for (int it = 0; it < n_it; ++it) {
+    constexpr int LAG = (SKEW && MASK != 0) ? 1 : 0;       // groups between a frame entering and leaving
+    for (int it = 0; it < n_it + LAG; ++it) {              // the extra iteration drains the pipeline (its input is not used)
         uint4 nn = nxt;
         if (it + 2 < n_it) nn = ldg16(src + it + 2);
         double nL[4] = {0, 0, 0, 0}, nR[4] = {0, 0, 0, 0};
         if (WARM) fetch_lut(nxt, nL, nR);
-        const int64_t g = g0f + 4 * (int64_t)it;
+        const int64_t g = g0f + 4 * (int64_t)(it - LAG);   // first frame of the group that leaves in this iteration
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k]);
-        if (g >= job.tile_begin && g + 4 <= f_hi) {
-            dst[it] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (it < LAG) {
+        } else if (g >= job.tile_begin && g + 4 <= f_hi) {
+            dst[it - LAG] = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it)[k] = o[k];
+                if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it - LAG)[k] = o[k];
         }
         cur = nxt; nxt = nn;
 #pragma unroll
@@ -281,7 +301,7 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     }
 }
 
-#define AME_EQ_KERNEL(NAME, F)                                                                                     \
+#define AME_EQ_KERNEL(NAME, F, SK)                                                                                  \
 __global__ void __launch_bounds__(128, 2)                                                                          \
 NAME(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,                    \
      const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {                 \
@@ -291,15 +311,16 @@ NAME(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__res
     if (job.tile_end <= job.tile_begin) return;           /* padding job (tracks get whole warps) */               \
     const ame_track_params *tp = tracks + job.track;                                                               \
     switch (job.variant) {      /* bits 0-3: EQ stages, bit 4: warmth */                                           \
-        AME_EQ_CASE(0, F) AME_EQ_CASE(1, F) AME_EQ_CASE(2, F) AME_EQ_CASE(3, F) AME_EQ_CASE(4, F) AME_EQ_CASE(5, F) \
-        AME_EQ_CASE(6, F) AME_EQ_CASE(7, F) AME_EQ_CASE(8, F) AME_EQ_CASE(9, F) AME_EQ_CASE(10, F) AME_EQ_CASE(11, F) \
-        AME_EQ_CASE(12, F) AME_EQ_CASE(13, F) AME_EQ_CASE(14, F) AME_EQ_CASE(15, F)                                 \
+        AME_EQ_CASE(0, F, SK) AME_EQ_CASE(1, F, SK) AME_EQ_CASE(2, F, SK) AME_EQ_CASE(3, F, SK) AME_EQ_CASE(4, F, SK)    \
+        AME_EQ_CASE(5, F, SK) AME_EQ_CASE(6, F, SK) AME_EQ_CASE(7, F, SK) AME_EQ_CASE(8, F, SK) AME_EQ_CASE(9, F, SK)    \
+        AME_EQ_CASE(10, F, SK) AME_EQ_CASE(11, F, SK) AME_EQ_CASE(12, F, SK) AME_EQ_CASE(13, F, SK) AME_EQ_CASE(14, F, SK) \
+        AME_EQ_CASE(15, F, SK)                                                                                     \
     }                                                                                                              \
 }
-#define AME_EQ_CASE(M, F) case M: eq_tile<M, false, F>(job, tp, luts, in, pre); break; \
-                          case M + 16: eq_tile<M, true, F>(job, tp, luts, in, pre); break;
-AME_EQ_KERNEL(k_eq, double)
-AME_EQ_KERNEL(k_eq_f32, float)      // precision experiment only (ame_plan_options.precision = 1)
+#define AME_EQ_CASE(M, F, SK) case M: eq_tile<M, false, F, SK>(job, tp, luts, in, pre); break; \
+                              case M + 16: eq_tile<M, true, F, SK>(job, tp, luts, in, pre); break;
+AME_EQ_KERNEL(k_eq, double, false)
+AME_EQ_KERNEL(k_eq_f32, float, false)      // precision experiment only (ame_plan_options.precision = 1)
 #undef AME_EQ_CASE
 #undef AME_EQ_KERNEL
 
@@ -846,11 +867,11 @@ k_att_chain(const ChainJob *__restrict__ jobs, const uint16_t *__restrict__ list
     if (stats && t == 0) { stats[2 * blockIdx.x] = (int)min(n_f, (int64_t)0x7fffffff); stats[2 * blockIdx.x + 1] = passes; }
 }
 
-__device__ __forceinline__ int mul_floor(int x, double f) {   // audioop.c fbound()
-    double v = __dmul_rn((double)x, f);
-    if (v > 32767.0) v = 32767.0;
-    else if (v < -32767.0) v = -32768.0;
-    return __double2int_rd(v);
+// audioop.mul: fbound(x * f) = floor(clamp(x * f)).  Here 0 < f <= 1 (f = 10^(-att/20), att > 0) and |x| <= 32768, so
+// |x * f| <= 32768: the upper clamp never binds and the lower one only replaces a value in (-32768, -32767) by -32768,
+// which floor() yields anyway.  (The max() is a guard against an exp10 one ulp above 1.0, not a case that occurs.)
+__device__ __forceinline__ int mul_floor(int x, double f) {
+    return max(__double2int_rd(__dmul_rn((double)x, f)), -32768);
 }
 
 // pydub db_to_float(-att) = 10 ** (-att / 20); out of line so the call sites of k_compress_apply share one copy
