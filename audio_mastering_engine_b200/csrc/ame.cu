@@ -184,7 +184,7 @@ struct ame_plan {
     KwJob *d_kw_jobs = nullptr;
     GainJob *d_gain_jobs = nullptr;
     AttEntry *d_tables = nullptr;
-    double *d_luts = nullptr;
+    float *d_luts = nullptr;
     int n_luts = 0;
     int16_t *d_in = nullptr, *d_out = nullptr;
     std::vector<Slot> slots;
@@ -470,10 +470,9 @@ int chain_lanes(const ame_plan *p, int n_chains) {
 int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     if (!w.chain_n) return AME_OK;
     t_begin(p, S_FLAG, s);
-    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, b.bands, b.rms, p->mb_frames, b.tile_cnt);
+    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, b.bands, b.rms, b.tile_cnt);
     LAUNCH_CHECK(p);
-    k_compact<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, p->d_chain_jobs, w.chain_lo, b.rms, b.tile_cnt, b.list, b.grp,
-                                            b.n_flagged, p->mb_frames);
+    k_compact<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, w.chain_lo, b.rms, b.tile_cnt, b.list, b.grp, b.n_flagged);
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
@@ -877,7 +876,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.wf_lo = (int)wf_jobs.size();
         for (int c = wv.chain_lo; c < (int)chain_jobs.size(); ++c) {
             chain_jobs[c].tile0 = (int)wf_jobs.size() - wv.wf_lo;
-            for (int64_t tb = 0; tb < chain_jobs[c].n; tb += kWfTile) wf_jobs.push_back(WfJob{c, 0, tb});
+            const ChainJob &cj = chain_jobs[c];
+            for (int64_t tb = 0; tb < cj.n; tb += kWfTile)
+                wf_jobs.push_back(WfJob{tb, (int64_t)cj.band * p->mb_frames + cj.mb_begin, cj.n, cj.grp_begin, c, cj.look, cj.thr_i, cj.tile0});
         }
         wv.eq_n = (int)eq_jobs.size() - wv.eq_lo; wv.split_n = (int)split_jobs.size() - wv.split_lo;
         wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
@@ -979,15 +980,12 @@ int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
         CU(cudaDeviceSynchronize());
         dev_free(p->d_luts);
         p->d_luts = nullptr;
-        p->ws_bytes -= (size_t)p->n_luts * 65536 * sizeof(double);
+        p->ws_bytes -= (size_t)p->n_luts * 65536 * sizeof(float);
         p->n_luts = 0;
     }
-    // widened exactly to double on the host so the kernel needs no float->double conversion per sample
-    std::vector<double> wide((size_t)n_luts * 65536);
-    for (size_t i = 0; i < wide.size(); ++i) wide[i] = (double)luts[i];
-    int rc = dmalloc(p, (void **)&p->d_luts, wide.size() * sizeof(double));
+    int rc = dmalloc(p, (void **)&p->d_luts, (size_t)n_luts * 65536 * sizeof(float));
     if (rc) return rc;
-    CU(cudaMemcpy(p->d_luts, wide.data(), wide.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_luts, luts, (size_t)n_luts * 65536 * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaStreamSynchronize(0));
     p->n_luts = n_luts;
     return AME_OK;
