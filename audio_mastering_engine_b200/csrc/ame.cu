@@ -184,7 +184,7 @@ struct ame_plan {
     KwJob *d_kw_jobs = nullptr;
     GainJob *d_gain_jobs = nullptr;
     AttEntry *d_tables = nullptr;
-    float *d_luts = nullptr;
+    double *d_luts = nullptr;
     int n_luts = 0;
     int16_t *d_in = nullptr, *d_out = nullptr;
     std::vector<Slot> slots;
@@ -980,12 +980,15 @@ int ame_plan_set_warm_luts(ame_plan *p, const float *luts, int32_t n_luts) {
         CU(cudaDeviceSynchronize());
         dev_free(p->d_luts);
         p->d_luts = nullptr;
-        p->ws_bytes -= (size_t)p->n_luts * 65536 * sizeof(float);
+        p->ws_bytes -= (size_t)p->n_luts * 65536 * sizeof(double);
         p->n_luts = 0;
     }
-    int rc = dmalloc(p, (void **)&p->d_luts, (size_t)n_luts * 65536 * sizeof(float));
+    // widened exactly to double on the host so the kernel needs no float->double conversion per sample
+    std::vector<double> wide((size_t)n_luts * 65536);
+    for (size_t i = 0; i < wide.size(); ++i) wide[i] = (double)luts[i];
+    int rc = dmalloc(p, (void **)&p->d_luts, wide.size() * sizeof(double));
     if (rc) return rc;
-    CU(cudaMemcpy(p->d_luts, luts, (size_t)n_luts * 65536 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_luts, wide.data(), wide.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaStreamSynchronize(0));
     p->n_luts = n_luts;
     return AME_OK;

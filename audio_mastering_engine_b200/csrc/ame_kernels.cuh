@@ -60,13 +60,7 @@ __constant__ double c_hist_bounds[1001];
 __constant__ double c_hist_energy[1000];
 
 // ------------------------------------------------------------------------------------------------
-// streaming 16-byte load; the L2 is asked for the whole 128-byte line (every lane walks its own tile, 16 or 32 bytes
-// per iteration: the next iterations' sectors of the line are then already on their way from DRAM)
-__device__ __forceinline__ uint4 ldg16(const uint4 *p) {
-    uint4 v;
-    asm("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
+__device__ __forceinline__ uint4 ldg16(const uint4 *p) { return __ldg(p); }
 
 __device__ __forceinline__ double bq_step(const ame_biquad &c, double &z0, double &z1, double x) {
     // DF-II transposed, the form scipy evaluates (lfilter / sosfilt) - FMA-contracted.
@@ -164,11 +158,11 @@ __device__ __forceinline__ double i16_to_unit(int x) {
 // 128-track launch (profiles/r02/summary.md): the compiler's schedule of the plain loop already overlaps the stages.
 template <int MASK, bool WARM, typename F, bool SKEW>
 __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_params *__restrict__ tp,
-                                        const float *__restrict__ luts, const int16_t *__restrict__ in,
+                                        const double *__restrict__ luts, const int16_t *__restrict__ in,
                                         int16_t *__restrict__ pre) {
     const bool widen = (tp->flags & AME_F_WIDTH) != 0;
     const float wfac = tp->width;
-    const float *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
+    const double *lut = WARM ? luts + (size_t)tp->warm_lut * 65536 + 32768 : nullptr;
     double wl_b0 = 0, wl_b1 = 0, wl_a1 = 0, wl_gm1 = 0, wh_b0 = 0, wh_b1 = 0, wh_a1 = 0, wh_gm1 = 0;
     if (WARM) {
         wl_b0 = tp->wl_b0; wl_b1 = tp->wl_b1; wl_a1 = tp->wl_a1; wl_gm1 = tp->wl_gm1;
@@ -221,13 +215,13 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
     F q0l = 0, q0r = 0, q1l = 0, q1r = 0, q2l = 0, q2r = 0, q3l = 0, q3r = 0;     // SKEW: stage outputs of the last four frames
 
     // one frame -> packed (L | R << 16) int16 output.  lutL / lutR = tanh table values (fetched a group ahead).
-    auto frame = [&](uint32_t w, float lutL, float lutR) -> uint32_t {
+    auto frame = [&](uint32_t w, double lutL, double lutR) -> uint32_t {
         int xl = (int)(int16_t)(w & 0xffffu), xr = (int)(int16_t)(w >> 16);
         if (WARM) {
             // apply_analog_character (:258-266): tanh in float32 (table = the host's own np.tanh, widened
             // exactly to double), then two order-2 "shelves" that lfilter(axis=-1) runs ACROSS the channels:
             //   y0 = b0*L ; y1 = (b1*L - a1*y0) + b0*R ; blend x + (y - x)*(g - 1)       (no FMA contraction)
-            double L = (double)lutL, R = (double)lutR;      // the float32 tanh value, widened exactly (:263 -> :286)
+            double L = lutL, R = lutR;
             double y0 = __dmul_rn(wl_b0, L);
             double y1 = __dadd_rn(__dsub_rn(__dmul_rn(wl_b1, L), __dmul_rn(wl_a1, y0)), __dmul_rn(wl_b0, R));
             const double L1 = __dadd_rn(L, __dmul_rn(__dsub_rn(y0, L), wl_gm1));
@@ -266,17 +260,14 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
 
     const uint4 *src = reinterpret_cast<const uint4 *>(in) + (g0f >> 2);
     uint4 *dst = reinterpret_cast<uint4 *>(pre) + (g0f >> 2);
-    // software pipeline: input words three groups ahead, tanh-table values (one 4-byte gather per sample, L2 / L1) two
-    // groups ahead - as float32, half the registers of the widened value, so that the compiler keeps them in flight
-    // instead of sinking the gathers to their use (ncu r02f: 9 % of the warmth variants' samples were long_scoreboard
-    // stalls on the first use of a table value)
-    auto load_group = [&](int i) -> uint4 { return i < n_it ? ldg16(src + i) : make_uint4(0, 0, 0, 0); };
-    uint4 w0 = load_group(0), w1 = load_group(1), w2 = load_group(2);
-    if (g0f + 0 < job.chunk_begin) w0.x = 0;               // frames before the chunk start keep the zero state
-    if (g0f + 1 < job.chunk_begin) w0.y = 0;
-    if (g0f + 2 < job.chunk_begin) w0.z = 0;
-    float l0[4] = {0, 0, 0, 0}, r0[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0}, r1[4] = {0, 0, 0, 0};
-    auto fetch_lut = [&](const uint4 &q, float *l, float *r) {
+    // software pipeline: input words two groups ahead, tanh-table values one group ahead
+    uint4 cur = ldg16(src), nxt = make_uint4(0, 0, 0, 0);
+    if (g0f + 0 < job.chunk_begin) cur.x = 0;              // frames before the chunk start keep the zero state
+    if (g0f + 1 < job.chunk_begin) cur.y = 0;
+    if (g0f + 2 < job.chunk_begin) cur.z = 0;
+    if (n_it > 1) nxt = ldg16(src + 1);
+    double lutL[4] = {0, 0, 0, 0}, lutR[4] = {0, 0, 0, 0};
+    auto fetch_lut = [&](const uint4 &q, double *l, double *r) {
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -284,17 +275,18 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
             r[k] = __ldg(lut + (int)(int16_t)(w[k] >> 16));
         }
     };
-    if (WARM) { fetch_lut(w0, l0, r0); fetch_lut(w1, l1, r1); }
+    if (WARM) fetch_lut(cur, lutL, lutR);
     constexpr int LAG = (SKEW && MASK != 0) ? 1 : 0;       // groups between a frame entering and leaving
     for (int it = 0; it < n_it + LAG; ++it) {              // the extra iteration drains the pipeline (its input is not used)
-        const uint4 w3 = load_group(it + 3);
-        float l2[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0};
-        if (WARM) fetch_lut(w2, l2, r2);
+        uint4 nn = nxt;
+        if (it + 2 < n_it) nn = ldg16(src + it + 2);
+        double nL[4] = {0, 0, 0, 0}, nR[4] = {0, 0, 0, 0};
+        if (WARM) fetch_lut(nxt, nL, nR);
         const int64_t g = g0f + 4 * (int64_t)(it - LAG);   // first frame of the group that leaves in this iteration
-        const uint32_t w[4] = {w0.x, w0.y, w0.z, w0.w};
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], l0[k], r0[k]);
+        for (int k = 0; k < 4; ++k) o[k] = frame(w[k], lutL[k], lutR[k]);
         if (it < LAG) {
         } else if (g >= job.tile_begin && g + 4 <= f_hi) {
             dst[it - LAG] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -303,16 +295,16 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
             for (int k = 0; k < 4; ++k)
                 if (g + k >= job.tile_begin && g + k < f_hi) reinterpret_cast<uint32_t *>(dst + it - LAG)[k] = o[k];
         }
-        w0 = w1; w1 = w2; w2 = w3;
+        cur = nxt; nxt = nn;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { l0[k] = l1[k]; r0[k] = r1[k]; l1[k] = l2[k]; r1[k] = r2[k]; }
+        for (int k = 0; k < 4; ++k) { lutL[k] = nL[k]; lutR[k] = nR[k]; }
     }
 }
 
 #define AME_EQ_KERNEL(NAME, F, SK)                                                                                  \
 __global__ void __launch_bounds__(128, 2)                                                                          \
 NAME(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,                    \
-     const float *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {                  \
+     const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {                 \
     const int j = blockIdx.x * blockDim.x + threadIdx.x;                                                           \
     if (j >= n_jobs) return;                                                                                       \
     const TileJob job = jobs[j];                                                                                   \
@@ -437,8 +429,8 @@ k_band_split(const __grid_constant__ XoverCfg xc, const TileJob *__restrict__ jo
 // only flagged frames take the square root (S/n is never within 2^-41 of a perfect square unless equal,
 // hence the double-precision expression of audioop truncates to the exact integer root).
 // ------------------------------------------------------------------------------------------------
-constexpr int kWfThreads = 512;
-constexpr int kWfTile = 4096;      // frames per CTA of k_window_flag / k_compact (8 per thread)
+constexpr int kWfThreads = 256;
+constexpr int kWfTile = 2048;      // frames per CTA of k_window_flag / k_compact (8 per thread)
 constexpr int kSeg = 256;          // frames per k_att_chain iteration / per k_compress_apply warp (8 groups)
 
 // One tile of a chain for k_window_flag / k_compact.  It carries what the kernels need of its chain, so a CTA (which
