@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--tracks-per-gpu", type=int, default=0, help="weak-scaling variant: this many tracks on every GPU")
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--fs", type=int, default=48000)
-    ap.add_argument("--wave-tracks", type=int, default=32, help="tracks per plan wave")
+    ap.add_argument("--wave-tracks", type=int, default=0, help="tracks per plan wave (0 = 32, or a sixth of the rank's tracks if fewer than 192)")
     ap.add_argument("--slots", type=int, default=6, help="workspace slots = waves in flight")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-wave-tracks", type=int, default=8)
@@ -289,7 +289,8 @@ def run_b200(args, rank, world, local_rank):
         n_tr, first = len(mine), mine.start
     ids = batch_order(list(range(first, first + n_tr)), synth, EQ_PRESETS)
     settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
-    n_waves = max(1, -(-n_tr // max(args.wave_tracks, 1)))
+    wave_tracks = args.wave_tracks if args.wave_tracks > 0 else (32 if n_tr >= 192 else max(1, -(-n_tr // 6)))
+    n_waves = max(1, -(-n_tr // wave_tracks))
     plan_kw = dict(device=local_rank, chain_warps=args.chain_warps, kw_tile_subblocks=args.kw_tile,
                    eq_tile_frames=args.eq_tile, xover_tile_frames=args.xover_tile, precision=args.precision)
     plan = MasterPlan([n] * n_tr, fs, settings, n_waves=n_waves, n_slots=args.slots, **plan_kw)
