@@ -527,7 +527,7 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
     t_begin(p, S_FIN, s);
-    k_finalize<<<(nt + 63) / 64, 64, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_hist_st, p->d_peak,
+    k_finalize<<<nt, 128, 0, s>>>(p->d_tracks, w.track_lo, w.track_hi, (const long long *)d_hist, p->d_hist_st, p->d_peak,
                                              p->d_tp, p->d_results);
     LAUNCH_CHECK(p);
     t_end(p, S_FIN, s);

@@ -1071,13 +1071,24 @@ k_block_hist(const TrackDev *__restrict__ tdev, int track_lo, const double *__re
     }
 }
 
-// k_finalize: ebur128_gated_loudness + loudness range + the linear-mode gain of af_loudnorm, one thread per track
-__global__ void k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_hi,
-                           const long long *__restrict__ hist, const int *__restrict__ hist_st, const int *__restrict__ peak,
-                           const unsigned *__restrict__ tp_bits, ame_track_result *__restrict__ res) {
-    const int t = track_lo + blockIdx.x * blockDim.x + threadIdx.x;
+// k_finalize: ebur128_gated_loudness + loudness range + the linear-mode gain of af_loudnorm.  One CTA per track: the
+// two 1000-bin histograms are staged in shared memory by all threads, then ONE thread walks them in the order
+// ebur128.c does (the sums are order-sensitive in the last bit, and that bit can decide the '%.2f' the gain is made of).
+__global__ void __launch_bounds__(128)
+k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_hi,
+           const long long *__restrict__ hist, const int *__restrict__ hist_st, const int *__restrict__ peak,
+           const unsigned *__restrict__ tp_bits, ame_track_result *__restrict__ res) {
+    __shared__ long long s_h[1000];
+    __shared__ int s_hs[1000];
+    const int t = track_lo + blockIdx.x;
     if (t >= track_hi) return;
-    const long long *h = hist + (int64_t)t * 1000;
+    for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
+        s_h[i] = hist[(int64_t)t * 1000 + i];
+        s_hs[i] = hist_st[(int64_t)t * 1000 + i];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const long long *h = s_h;
     ame_track_result r;
     r.input_i = -INFINITY; r.measured_i_2dp = -INFINITY; r.gain = 1.0; r.rel_threshold = 0.0;
     r.n_blocks = 0; r.normalized = 0; r.sample_peak = peak[t];
@@ -1109,7 +1120,7 @@ __global__ void k_finalize(const ame_track_params *__restrict__ tracks, int trac
     }
     // ff_ebur128_loudness_range: short-term blocks above (mean power - 20 dB), 10th .. 95th percentile
     {
-        const int *hs = hist_st + (int64_t)t * 1000;
+        const int *hs = s_hs;
         long long n = 0; double power = 0.0;
         for (int j = 0; j < 1000; ++j) { n += hs[j]; power += (double)hs[j] * c_hist_energy[j]; }
         if (n > 0) {
