@@ -150,6 +150,8 @@ struct Slot {
     double *att = nullptr;       // 3 planes: attenuation after every flagged frame, dense per chain
     int16_t *norm = nullptr;     // the normalised signal of tracks with the limiter stage (k_apply_gain -> k_limiter)
     long long *lim_last = nullptr;   // per k_apply_gain tile: last frame over the limiter's limit, or -1
+    LimState *lim_in = nullptr, *lim_out = nullptr;   // per tile: the limiter state it started from / ended in
+    int *lim_need = nullptr;         // per tile: its start is not its predecessor's end (yet)
     cudaStream_t stream = nullptr;
 };
 
@@ -417,6 +419,8 @@ struct Bufs {
     int64_t *hist = nullptr;
     int16_t *norm = nullptr;
     long long *lim_last = nullptr;
+    LimState *lim_in = nullptr, *lim_out = nullptr;
+    int *lim_need = nullptr;
 };
 
 Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) {
@@ -427,7 +431,7 @@ Bufs slot_bufs(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_out) 
     b.bands = sl.bands; b.rms = sl.rms; b.list = sl.list; b.tile_cnt = sl.tile_cnt; b.n_flagged = sl.n_flagged;
     b.grp = sl.grp; b.att = sl.att;
     b.norm = sl.norm ? sl.norm - 2 * w.frame_lo : nullptr;
-    b.lim_last = sl.lim_last;
+    b.lim_last = sl.lim_last; b.lim_in = sl.lim_in; b.lim_out = sl.lim_out; b.lim_need = sl.lim_need;
     b.hist = (int64_t *)p->d_hist;
     return b;
 }
@@ -522,8 +526,9 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     return AME_OK;
 }
 
-int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, int16_t *d_norm,
-             long long *lim_last, cudaStream_t s) {
+int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, const Bufs &b, cudaStream_t s) {
+    int16_t *d_norm = b.norm;
+    long long *lim_last = b.lim_last;
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
     t_begin(p, S_FIN, s);
@@ -538,7 +543,15 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
         t_end(p, S_GAIN, s);
         if (w.limiter) {
             t_begin(p, S_LIM, s);
-            k_limiter<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, w.gain_n, lim_last, p->d_tracks, d_norm, d_out);
+            const GainJob *gj = p->d_gain_jobs + w.gain_lo;
+            constexpr int kLimRounds = 2;                 // repair rounds before the sequential fallback
+            for (int round = 0; round <= kLimRounds; ++round) {
+                k_limiter<<<w.gain_n, 256, 0, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round);
+                LAUNCH_CHECK(p);
+                k_lim_verify<<<(w.gain_n + 127) / 128, 128, 0, s>>>(gj, w.gain_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need);
+                LAUNCH_CHECK(p);
+            }
+            k_lim_fallback<<<w.gain_n, 32, 0, s>>>(gj, w.gain_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need);
             LAUNCH_CHECK(p);
             t_end(p, S_LIM, s);
         }
@@ -557,7 +570,7 @@ int run_measure(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
 int run_chain_of_stages(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     int rc = run_measure(p, w, b, s);
     if (rc) return rc;
-    return run_gain(p, w, b.pre, b.hist, b.out, b.norm, b.lim_last, s);
+    return run_gain(p, w, b.pre, b.hist, b.out, b, s);
 }
 
 // after a failure in the middle of a pipelined call nothing may still be reading the caller's buffers when we return
@@ -596,7 +609,8 @@ void ame_plan_destroy(ame_plan *p) {
     for (void *q : ptrs) dev_free(q);
     for (Slot &sl : p->slots) {
         for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.list, (void *)sl.tile_cnt, (void *)sl.n_flagged,
-                        (void *)sl.grp, (void *)sl.att, (void *)sl.norm, (void *)sl.lim_last})
+                        (void *)sl.grp, (void *)sl.att, (void *)sl.norm, (void *)sl.lim_last, (void *)sl.lim_in, (void *)sl.lim_out,
+                        (void *)sl.lim_need})
             dev_free(q);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -910,7 +924,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             return bail(rc);
         if (p->any_limiter &&
             ((rc = dmalloc(p, (void **)&sl.norm, (size_t)p->slot_frames * 4)) ||
-             (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(long long)))))
+             (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(long long))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_need, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(int)))))
             return bail(rc);
         // the filters read a few frames past a track's end (whole 16 / 32-byte groups, never stored): keep them defined
         if (cudaMemsetAsync(sl.pre, 0, (size_t)p->slot_frames * 4, 0) != cudaSuccess ||
@@ -1122,7 +1139,7 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
     GUARD(p->device);
     cudaStream_t s = (cudaStream_t)stream;
     const Bufs sb = slot_bufs(p, p->waves[0], nullptr, d_out);
-    int rc = run_gain(p, p->waves[0], d_pre, d_hist, d_out, sb.norm, sb.lim_last, s);
+    int rc = run_gain(p, p->waves[0], d_pre, d_hist, d_out, sb, s);
     if (rc) return rc;
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));
@@ -1158,7 +1175,7 @@ int ame_normalize_device(ame_plan *p, const int64_t *d_hist, int16_t *d_out, ame
     for (size_t w = 0; w < p->waves.size(); ++w) {
         p->t_wave = (int)std::min<size_t>(w, kMaxTimedWaves - 1);
         const Bufs b = slot_bufs(p, p->waves[w], nullptr, d_out);
-        if ((rc = run_gain(p, p->waves[w], b.pre, d_hist, d_out, b.norm, b.lim_last, s))) return rc;
+        if ((rc = run_gain(p, p->waves[w], b.pre, d_hist, d_out, b, s))) return rc;
     }
     if (results) {
         CU(cudaMemcpyAsync(results, p->d_results, (size_t)p->n_tracks * sizeof(ame_track_result), cudaMemcpyDeviceToHost, s));

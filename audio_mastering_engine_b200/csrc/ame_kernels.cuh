@@ -1193,23 +1193,55 @@ k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_limiter: ffmpeg alimiter (audio_mastering_engine.py:223; af_alimiter.c with level_in = level_out = 1, auto level
-// on, asc off, latency off) on the normalised signal.  The filter is one sequential state machine per track:
-// a look-ahead ring of B frames (output = input delayed by B - 1 frames), an attenuation `att` that moves by `delta`
-// per frame, and a queue of the over-limit peaks inside the ring with the slope each will hand over when it leaves.
-// What makes it parallel in time: after G = B + release_frames + 8 frames without an over-limit frame the state is
-// the initial one again (att 1, delta 0, empty queue - the last queued peak has left the ring and its linear release
-// has reached 1), and in that state the filter is elementwise: out[n] = clip(x[n - B + 1]) / limit.
-// One CTA per k_apply_gain tile (32768 frames >= G):
-//   * a tile that starts in the initial state (no over-limit frame in the G frames before it: k_apply_gain left
-//     the previous tile's last over-limit frame) and has no over-limit frame of its own is done elementwise by all
-//     256 threads;
-//   * a tile that starts in the initial state and has over-limit frames makes warp 0 the sequential machine from its
-//     first frame up to the next tile that starts in the initial state (lane 0 walks the attenuation 32 frames at a
-//     time, all lanes load the frames before and scale / round / store them after);
-//   * every other tile is covered by such a run and its CTA leaves at once.
+// ffmpeg alimiter (audio_mastering_engine.py:223; af_alimiter.c with level_in = level_out = 1, auto level on, asc off,
+// latency off) on the normalised signal.  The filter is one sequential state machine per track: a look-ahead ring of B
+// frames (output = input delayed by B - 1 frames), an attenuation `att` that moves by `delta` per frame, and a queue of
+// the over-limit peaks inside the ring with the slope each will hand over when it leaves.
+// What makes it parallel in time:
+//   (1) after G = B + release_frames + 8 frames without an over-limit frame the state is the initial one again (att 1,
+//       delta 0, empty queue: the last queued peak has left the ring and its linear release has reached 1), and in that
+//       state the filter is elementwise, out[n] = clip(x[n - B + 1]) / limit.  k_apply_gain leaves per 32768-frame tile
+//       the last frame over the limit, so every tile knows whether it STARTS in the initial state and whether it is
+//       elementwise throughout (all 256 threads, copy speed - the common case for mastered material);
+//   (2) a tile that does not start in the initial state (a track that is over the limit all the time - a hot loudness
+//       target clips) takes a GUESS of its start state: the machine run from the initial state over the 2 G frames in
+//       front of the tile.  The machine forgets: when a queued peak leaves the ring the attenuation is SET to
+//       limit / peak, and everything else in the state (slope, queue) is made of peaks inside the ring.  Every tile
+//       records the state it started from and the state it ended in; k_lim_verify compares each tile's start with its
+//       predecessor's end, field by field and bit by bit; a tile whose guess was wrong runs again from its
+//       predecessor's end (two rounds), and what is still open after that is walked sequentially by k_lim_fallback
+//       until the live state equals a recorded start.  When every start equals its predecessor's end, the tiles are
+//       the sequential run: exact.
+// One warp per non-elementwise tile: lane 0 walks the state 32 frames at a time, all lanes load the frames before and
+// scale / round / store them after.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLimQueue = 1024;     // queue capacity >= B + 2 (B <= 1000 frames is validated by the host)
+constexpr int kLimKeep = 8;         // queue entries a recorded state can hold (more: the state is "not representable")
+
+struct LimState {                   // the machine between two frames
+    double att, delta;
+    int qlen;                       // -1: more than kLimKeep entries, cannot be compared / resumed
+    int exact;                      // as a tile's START state: known to be the true one (initial state / track start)
+    int qframe[kLimKeep];           // frame (relative to the track) of every queued peak, in queue order
+    double qdelta[kLimKeep];
+};
+
+struct LimSmem {
+    int qframe[kLimQueue];          // -1 = none (the sentinel af_alimiter.c keeps behind the last entry)
+    double qdelta[kLimQueue];
+    double att[32];
+    int pin[32], pout[32];          // peak (max |s16|) of the frame entering / leaving the ring at each of 32 steps
+};
+
+struct LimCtx {
+    const uint32_t *x;              // normalised signal (packed buffer)
+    uint32_t *y;                    // output
+    int64_t t_begin, t_end;         // the track
+    int B, thr_i;
+    double limit, level, fsrel;
+};
+
+struct LimRegs { double att, delta; int qiter, qlen; };      // lane 0's part of the machine
 
 __device__ __forceinline__ int lim_out_sample(int x, double att, double limit, double level) {
     double v = __dmul_rn((double)x * (1.0 / 32768.0), att);          // buf[c] * att
@@ -1218,117 +1250,239 @@ __device__ __forceinline__ int lim_out_sample(int x, double att, double limit, d
     return sat16(__double2int_rn(__dmul_rn(v, 32768.0)));             // swresample dbl -> s16
 }
 
-__global__ void __launch_bounds__(256)
-k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restrict__ lim_last,
-          const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ norm, int16_t *__restrict__ out) {
-    __shared__ int s_qframe[kLimQueue];           // frame (relative to the track start) of every queued peak, -1 = none
-    __shared__ double s_qdelta[kLimQueue];
-    __shared__ double s_att[32];
-    __shared__ int s_pin[32], s_pout[32];         // peak (max |s16|) of the frame entering / leaving the ring at each step
-    const GainJob job = jobs[blockIdx.x];
-    const ame_track_params *tp = tracks + job.track;
-    if (!(tp->flags & AME_F_LIMITER)) return;
-    const int B = tp->lim_frames;
-    const double limit = tp->lim_limit, level = tp->lim_level, fsrel = tp->lim_fs_release;
-    const int64_t G = (int64_t)B + tp->lim_release_frames + 8;
-    const int64_t t_begin = tp->offset_frames + tp->halo_frames, t_end = t_begin + tp->n_frames;
-    const bool first = blockIdx.x == 0 || jobs[blockIdx.x - 1].track != job.track;
-    const long long prev_last = first ? -1 : lim_last[blockIdx.x - 1];
-    const bool quiet_start = first || prev_last < 0 || (job.begin - 1 - prev_last >= G);
-    if (!quiet_start) return;                                         // inside some earlier tile's sequential run
-    const uint32_t *x = reinterpret_cast<const uint32_t *>(norm);
-    uint32_t *y = reinterpret_cast<uint32_t *>(out);
-    auto emit = [&](int64_t n, double att) {                          // output frame n = input frame n - (B - 1)
-        const int64_t m = n - (B - 1);
-        const uint32_t w = m >= t_begin ? __ldg(x + m) : 0u;
-        y[n] = pack16(lim_out_sample((int16_t)(w & 0xffffu), att, limit, level), lim_out_sample((int16_t)(w >> 16), att, limit, level));
-    };
-    if (lim_last[blockIdx.x] < 0) {                                   // initial state throughout: elementwise
-        for (int64_t n = job.begin + threadIdx.x; n < job.end; n += blockDim.x) emit(n, 1.0);
-        return;
-    }
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    const int thr_i = tp->lim_thr_i;
-    for (int i = lane; i < kLimQueue; i += 32) { s_qframe[i] = -1; s_qdelta[i] = 0.0; }
+__device__ __forceinline__ void lim_emit(const LimCtx &c, int64_t n, double att) {   // output frame n = input frame n - (B - 1)
+    const int64_t m = n - (c.B - 1);
+    const uint32_t w = m >= c.t_begin ? __ldg(c.x + m) : 0u;
+    c.y[n] = pack16(lim_out_sample((int16_t)(w & 0xffffu), att, c.limit, c.level), lim_out_sample((int16_t)(w >> 16), att, c.limit, c.level));
+}
+
+__device__ __forceinline__ void lim_reset(LimRegs &r, LimSmem &sm, int lane) {
+    for (int i = lane; i < kLimQueue; i += 32) { sm.qframe[i] = -1; sm.qdelta[i] = 0.0; }
+    r.att = 1.0; r.delta = 0.0; r.qiter = 0; r.qlen = 0;
     __syncwarp();
-    // lane 0's state (af_alimiter.c: att, delta, nextiter, nextlen; nextpos / nextdelta are s_qframe / s_qdelta)
-    double att = 1.0, delta = 0.0;
-    int qiter = 0, qlen = 0;
-    int64_t last_over = -1;
-    const int bufsize = 2 * B;
-    auto peak_of = [&](int64_t rel) -> double {                       // |sample| peak of a frame of the track, as the ring holds it
-        const uint32_t w = __ldg(x + t_begin + rel);
-        const int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
-        return (double)max(abs(l), abs(r)) * (1.0 / 32768.0);
-    };
-    bool done = false;
-    for (int64_t n0 = job.begin; n0 < t_end && !done; n0 += 32) {
-        const int64_t n = n0 + lane, m = n - (B - 1);
-        const uint32_t win = n < t_end ? __ldg(x + n) : 0u;
-        const uint32_t wout = (n < t_end && m >= t_begin) ? __ldg(x + m) : 0u;
-        s_pin[lane] = max(abs((int)(int16_t)(win & 0xffffu)), abs((int)(int16_t)(win >> 16)));
-        s_pout[lane] = max(abs((int)(int16_t)(wout & 0xffffu)), abs((int)(int16_t)(wout >> 16)));
-        const unsigned over = __ballot_sync(kFull, n < t_end && s_pin[lane] >= thr_i);
+}
+
+__device__ __forceinline__ void lim_save(const LimRegs &r, const LimSmem &sm, LimState *st, int exact) {   // lane 0
+    st->att = r.att; st->delta = r.delta; st->exact = exact;
+    st->qlen = r.qlen <= kLimKeep ? r.qlen : -1;
+    for (int k = 0; k < kLimKeep; ++k) {
+        const bool in = k < r.qlen;
+        st->qframe[k] = in ? sm.qframe[(r.qiter + k) % kLimQueue] : -1;
+        st->qdelta[k] = in ? sm.qdelta[(r.qiter + k) % kLimQueue] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void lim_load(LimRegs &r, LimSmem &sm, const LimState &st, int lane) {   // whole warp; st.qlen >= 0
+    lim_reset(r, sm, lane);
+    r.att = st.att; r.delta = st.delta; r.qiter = 0; r.qlen = st.qlen;
+    if (lane == 0)
+        for (int k = 0; k < st.qlen; ++k) { sm.qframe[k] = st.qframe[k]; sm.qdelta[k] = st.qdelta[k]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool lim_equal(const LimState &a, const LimState &b) {
+    if (a.qlen < 0 || b.qlen < 0 || a.qlen != b.qlen) return false;
+    if (__double_as_longlong(a.att) != __double_as_longlong(b.att) || __double_as_longlong(a.delta) != __double_as_longlong(b.delta)) return false;
+    for (int k = 0; k < a.qlen; ++k)
+        if (a.qframe[k] != b.qframe[k] || __double_as_longlong(a.qdelta[k]) != __double_as_longlong(b.qdelta[k])) return false;
+    return true;
+}
+
+// the machine over frames [n_lo, n_hi) of the packed buffer (whole warp); output is stored when `emit`
+__device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm, int64_t n_lo, int64_t n_hi, bool emit, int lane) {
+    const int bufsize = 2 * c.B;
+    for (int64_t n0 = n_lo; n0 < n_hi; n0 += 32) {
+        const int64_t n = n0 + lane, m = n - (c.B - 1);
+        const uint32_t win = n < n_hi ? __ldg(c.x + n) : 0u;
+        const uint32_t wout = (n < n_hi && m >= c.t_begin) ? __ldg(c.x + m) : 0u;
+        sm.pin[lane] = max(abs((int)(int16_t)(win & 0xffffu)), abs((int)(int16_t)(win >> 16)));
+        sm.pout[lane] = max(abs((int)(int16_t)(wout & 0xffffu)), abs((int)(int16_t)(wout >> 16)));
+        const unsigned over = __ballot_sync(kFull, n < n_hi && sm.pin[lane] >= c.thr_i);
         __syncwarp();
-        int n_valid = (int)min((int64_t)32, t_end - n0);
+        const int n_valid = (int)min((int64_t)32, n_hi - n0);
         if (lane == 0) {
-            for (int k = 0; k < n_valid; ++k) {
-                const int64_t nn = n0 + k;
-                const int rel = (int)(nn - t_begin);
-                if (over & (1u << k)) {                               // the entering frame is over the limit
-                    last_over = nn;
-                    const double peak = (double)s_pin[k] * (1.0 / 32768.0);
-                    const double patt = fmin(limit / peak, 1.0);
-                    const double rdelta = (1.0 - patt) / fsrel;
-                    const double d = (limit / peak - att) / bufsize * 2;
-                    if (d < delta) {
-                        delta = d;
-                        s_qframe[0] = rel; s_qframe[1] = -1; s_qdelta[0] = rdelta;
-                        qlen = 1; qiter = 0;
-                    } else {
-                        bool found = false;
-                        int i = qiter;
-                        for (; i < qiter + qlen; ++i) {
-                            const int j = i % kLimQueue;
-                            const double ppeak = peak_of(s_qframe[j]);
-                            const double pdelta = (limit / peak - limit / ppeak) / (double)(rel - s_qframe[j]);
-                            if (pdelta < s_qdelta[j]) { s_qdelta[j] = pdelta; found = true; break; }
-                        }
-                        if (found) {
-                            qlen = i - qiter + 1;
-                            s_qframe[(qiter + qlen) % kLimQueue] = rel;
-                            s_qdelta[(qiter + qlen) % kLimQueue] = rdelta;
-                            s_qframe[(qiter + qlen + 1) % kLimQueue] = -1;
-                            ++qlen;
+            double att = r.att, delta = r.delta;
+            int qiter = r.qiter, qlen = r.qlen;
+            if (over == 0 && qlen == 0 && delta == 0.0) {             // nothing can happen in these 32 frames
+                for (int k = 0; k < n_valid; ++k) sm.att[k] = att;
+            } else {
+                for (int k = 0; k < n_valid; ++k) {
+                    const int rel = (int)(n0 + k - c.t_begin);
+                    if (over & (1u << k)) {                           // the entering frame is over the limit
+                        const double peak = (double)sm.pin[k] * (1.0 / 32768.0);
+                        const double patt = fmin(c.limit / peak, 1.0);
+                        const double rdelta = (1.0 - patt) / c.fsrel;
+                        const double d = (c.limit / peak - att) / bufsize * 2;
+                        if (d < delta) {
+                            delta = d;
+                            sm.qframe[0] = rel; sm.qframe[1] = -1; sm.qdelta[0] = rdelta;
+                            qlen = 1; qiter = 0;
+                        } else {
+                            bool found = false;
+                            int i = qiter;
+                            for (; i < qiter + qlen; ++i) {
+                                const int j = i % kLimQueue;
+                                const uint32_t w = __ldg(c.x + c.t_begin + sm.qframe[j]);
+                                const double ppeak = (double)max(abs((int)(int16_t)(w & 0xffffu)), abs((int)(int16_t)(w >> 16))) * (1.0 / 32768.0);
+                                const double pdelta = (c.limit / peak - c.limit / ppeak) / (double)(rel - sm.qframe[j]);
+                                if (pdelta < sm.qdelta[j]) { sm.qdelta[j] = pdelta; found = true; break; }
+                            }
+                            if (found) {
+                                qlen = i - qiter + 1;
+                                sm.qframe[(qiter + qlen) % kLimQueue] = rel;
+                                sm.qdelta[(qiter + qlen) % kLimQueue] = rdelta;
+                                sm.qframe[(qiter + qlen + 1) % kLimQueue] = -1;
+                                ++qlen;
+                            }
                         }
                     }
-                }
-                att += delta;
-                s_att[k] = att;                                       // the leaving frame is scaled by this
-                if (rel >= B - 1 && rel - (B - 1) == s_qframe[qiter]) {   // a queued peak leaves the ring
-                    delta = s_qdelta[qiter];
-                    att = limit / ((double)s_pout[k] * (1.0 / 32768.0));
-                    --qlen;
-                    s_qframe[qiter] = -1;
-                    qiter = (qiter + 1) % kLimQueue;
-                }
-                if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; s_qframe[0] = -1; }
-                if (att <= 0.0) { att = 0.0000000000001; delta = (1.0 - att) / fsrel; }
-                if (att != 1.0 && (1.0 - att) < 0.0000000000001) att = 1.0;
-                if (delta != 0.0 && fabs(delta) < 0.00000000000001) delta = 0.0;
-                // end of a tile: does the next one start in the initial state?  (the same test its own CTA makes)
-                if ((nn + 1 - t_begin) % kGainTile == 0 && nn + 1 < t_end) {
-                    const int64_t tile_lo = nn + 1 - kGainTile;
-                    if (last_over < tile_lo || nn - last_over >= G) { n_valid = k + 1; done = true; break; }
+                    att += delta;
+                    sm.att[k] = att;                                  // the leaving frame is scaled by this
+                    if (rel >= c.B - 1 && rel - (c.B - 1) == sm.qframe[qiter]) {   // a queued peak leaves the ring
+                        delta = sm.qdelta[qiter];
+                        att = c.limit / ((double)sm.pout[k] * (1.0 / 32768.0));
+                        --qlen;
+                        sm.qframe[qiter] = -1;
+                        qiter = (qiter + 1) % kLimQueue;
+                    }
+                    if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; sm.qframe[0] = -1; }
+                    if (att <= 0.0) { att = 0.0000000000001; delta = (1.0 - att) / c.fsrel; }
+                    if (att != 1.0 && (1.0 - att) < 0.0000000000001) att = 1.0;
+                    if (delta != 0.0 && fabs(delta) < 0.00000000000001) delta = 0.0;
                 }
             }
+            r.att = att; r.delta = delta; r.qiter = qiter; r.qlen = qlen;
         }
-        n_valid = __shfl_sync(kFull, n_valid, 0);
-        done = __shfl_sync(kFull, (int)done, 0) != 0;
         __syncwarp();
-        if (lane < n_valid) emit(n, s_att[lane]);
+        if (emit && lane < n_valid) lim_emit(c, n, sm.att[lane]);
         __syncwarp();
+    }
+}
+
+struct LimTile { bool limiter, first, quiet_start, simple; int64_t G; };
+
+__device__ __forceinline__ LimTile lim_classify(const GainJob *jobs, int tile, const long long *lim_last, const ame_track_params *tp) {
+    LimTile t;
+    const GainJob job = jobs[tile];
+    t.limiter = (tp->flags & AME_F_LIMITER) != 0;
+    t.G = (int64_t)tp->lim_frames + tp->lim_release_frames + 8;
+    t.first = tile == 0 || jobs[tile - 1].track != job.track;
+    const long long prev_last = t.first ? -1 : lim_last[tile - 1];
+    t.quiet_start = t.first || prev_last < 0 || (job.begin - 1 - prev_last >= t.G);
+    t.simple = t.quiet_start && lim_last[tile] < 0;
+    return t;
+}
+
+__device__ __forceinline__ LimCtx lim_ctx(const ame_track_params *tp, const int16_t *norm, int16_t *out) {
+    LimCtx c;
+    c.x = reinterpret_cast<const uint32_t *>(norm);
+    c.y = reinterpret_cast<uint32_t *>(out);
+    c.t_begin = tp->offset_frames + tp->halo_frames;
+    c.t_end = c.t_begin + tp->n_frames;
+    c.B = tp->lim_frames; c.thr_i = tp->lim_thr_i;
+    c.limit = tp->lim_limit; c.level = tp->lim_level; c.fsrel = tp->lim_fs_release;
+    return c;
+}
+
+// round 0: every tile (elementwise tiles by all threads, the others by warp 0 from the initial state or from a guess);
+// round >= 1: the tiles k_lim_verify left open, from their predecessor's recorded end state
+__global__ void __launch_bounds__(256)
+k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restrict__ lim_last,
+          const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ norm, int16_t *__restrict__ out,
+          LimState *__restrict__ st_in, LimState *__restrict__ st_out, int *__restrict__ need, int round) {
+    __shared__ LimSmem sm;
+    const int tile = blockIdx.x;
+    const GainJob job = jobs[tile];
+    const ame_track_params *tp = tracks + job.track;
+    const LimTile t = lim_classify(jobs, tile, lim_last, tp);
+    if (!t.limiter) { if (round == 0 && threadIdx.x == 0) need[tile] = 0; return; }
+    const LimCtx c = lim_ctx(tp, norm, out);
+    const int lane = threadIdx.x & 31;
+    LimRegs r;
+    if (round == 0) {
+        if (t.simple) {                                               // initial state throughout: elementwise
+            for (int64_t n = job.begin + threadIdx.x; n < job.end; n += blockDim.x) lim_emit(c, n, 1.0);
+            if (threadIdx.x == 0) {
+                LimState z;
+                z.att = 1.0; z.delta = 0.0; z.qlen = 0; z.exact = 1;
+                for (int k = 0; k < kLimKeep; ++k) { z.qframe[k] = -1; z.qdelta[k] = 0.0; }
+                st_in[tile] = z; st_out[tile] = z; need[tile] = 0;
+            }
+            return;
+        }
+        if (threadIdx.x >= 32) return;
+        lim_reset(r, sm, lane);
+        int exact = 1;
+        if (!t.quiet_start) {                                         // guess: the machine over the 2 G frames in front
+            const int64_t ws = max(c.t_begin, job.begin - 2 * t.G);
+            exact = ws == c.t_begin;                                  // from the track start it is no guess
+            lim_run(c, r, sm, ws, job.begin, false, lane);
+        }
+        if (lane == 0) lim_save(r, sm, st_in + tile, exact);
+    } else {
+        // open, and the predecessor is settled (it does not run in this round, so its recorded end is stable)
+        if (threadIdx.x >= 32 || !need[tile] || need[tile - 1]) return;
+        const LimState pred = st_out[tile - 1];
+        if (pred.qlen < 0) return;                                    // k_lim_fallback's case
+        lim_load(r, sm, pred, lane);
+        if (lane == 0) { LimState s0 = pred; s0.exact = 0; st_in[tile] = s0; }
+    }
+    lim_run(c, r, sm, job.begin, job.end, true, lane);
+    if (lane == 0) lim_save(r, sm, st_out + tile, 0);
+}
+
+// does every tile start where its predecessor ended?
+__global__ void k_lim_verify(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+                             const LimState *__restrict__ st_in, const LimState *__restrict__ st_out, int *__restrict__ need) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= n_jobs) return;
+    const GainJob job = jobs[tile];
+    int open = 0;
+    if ((tracks[job.track].flags & AME_F_LIMITER) && tile > 0 && jobs[tile - 1].track == job.track && !st_in[tile].exact)
+        open = !lim_equal(st_in[tile], st_out[tile - 1]);
+    need[tile] = open;
+}
+
+// what the repair rounds left open: ONE warp per track walks its tiles in order; at an open tile it resumes from the
+// predecessor's end (or, if that state is not representable, silently from the last tile with an exact start) and keeps
+// walking until its live state equals the recorded start of a tile that is not open - from there on the recorded tiles
+// are the sequential run again
+__global__ void __launch_bounds__(32)
+k_lim_fallback(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+               const int16_t *__restrict__ norm, int16_t *__restrict__ out, LimState *__restrict__ st_in,
+               LimState *__restrict__ st_out, const int *__restrict__ need) {
+    __shared__ LimSmem sm;
+    __shared__ LimState live;
+    const int first_tile = blockIdx.x;
+    const int track = jobs[first_tile].track;
+    if (first_tile > 0 && jobs[first_tile - 1].track == track) return;       // not the first tile of its track
+    const ame_track_params *tp = tracks + track;
+    if (!(tp->flags & AME_F_LIMITER)) return;
+    const LimCtx c = lim_ctx(tp, norm, out);
+    const int lane = threadIdx.x;
+    LimRegs r;
+    bool walking = false;
+    for (int tile = first_tile; tile < n_jobs && jobs[tile].track == track; ++tile) {
+        if (!walking) {
+            if (!need[tile]) continue;
+            const LimState pred = st_out[tile - 1];                           // an open tile has a predecessor in its track
+            if (pred.qlen >= 0) {
+                lim_load(r, sm, pred, lane);
+            } else {
+                int j = tile - 1;
+                while (!st_in[j].exact) --j;                                  // the first tile of a track is exact
+                const LimState s0 = st_in[j];
+                lim_load(r, sm, s0, lane);
+                lim_run(c, r, sm, jobs[j].begin, jobs[tile].begin, false, lane);
+            }
+            walking = true;
+        }
+        lim_run(c, r, sm, jobs[tile].begin, jobs[tile].end, true, lane);
+        if (lane == 0) { lim_save(r, sm, st_out + tile, 0); lim_save(r, sm, &live, 0); }
+        __syncwarp();
+        const int next = tile + 1;
+        if (next < n_jobs && jobs[next].track == track && !need[next] && (st_in[next].exact || lim_equal(live, st_in[next])))
+            walking = false;
     }
 }
 

@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--eq-tile", type=int, default=0, help="ame_plan_options.eq_tile_frames (0 = auto)")
     ap.add_argument("--xover-tile", type=int, default=0, help="ame_plan_options.xover_tile_frames (0 = auto)")
     ap.add_argument("--precision", default="exact", choices=["exact", "fp32"])
+    ap.add_argument("--limiter", action="store_true", help="also run the final alimiter stage (:223; not part of north_star (a)-(d))")
+    ap.add_argument("--true-peak", action="store_true", help="also measure the BS.1770 true peak")
     return ap.parse_args()
 
 
@@ -288,7 +290,7 @@ def run_b200(args, rank, world, local_rank):
         mine = shard_tracks(total_tracks, world, rank)
         n_tr, first = len(mine), mine.start
     ids = batch_order(list(range(first, first + n_tr)), synth, EQ_PRESETS)
-    settings = [synth.c4_settings(t, EQ_PRESETS) for t in ids]
+    settings = [dict(synth.c4_settings(t, EQ_PRESETS), limiter=args.limiter, true_peak=args.true_peak) for t in ids]
     wave_tracks = args.wave_tracks if args.wave_tracks > 0 else (32 if n_tr >= 192 else max(1, -(-n_tr // 6)))
     n_waves = max(1, -(-n_tr // wave_tracks))
     plan_kw = dict(device=local_rank, chain_warps=args.chain_warps, kw_tile_subblocks=args.kw_tile,

@@ -388,7 +388,10 @@ def test_limiter_stage_is_bit_exact(torch_cuda):
     cases = [synth.track(1.0, fs, track_id=30) // 2,                   # nothing over the limit
              _hot(synth.track(1.5, fs, track_id=32, am_hz=3.0), 4.0),  # sparse peaks
              _hot(synth.track(2.0, fs, track_id=33, am_hz=2.0), 14.0), # clipped most of the time
-             long, long[:32768], long[:32769], long[:100]]
+             long, long[:32768], long[:32769], long[:100],
+             _hot(synth.track(14.0, fs, track_id=34, am_hz=1.0), 14.0),   # 21 tiles over the limit all the time: every start is a guess
+             _hot(synth.track(14.0, fs, track_id=35, am_hz=0.7, am_db=10.0), 5.0),   # busy and quiet passages alternate
+             _hot(synth.stress_track(11.0, fs, track_id=36), 3.5)]     # bursts, beds, zero gaps, clicks
     for k, x in enumerate(cases):
         plain, _ = master(x, fs, flat)
         got, _ = master(x, fs, dict(flat, limiter=True))
