@@ -150,7 +150,7 @@ struct Slot {
     double *att = nullptr;       // 3 planes: attenuation after every flagged frame, dense per chain
     int16_t *norm = nullptr;     // the normalised signal of tracks with the limiter stage (k_apply_gain -> k_limiter)
     long long *lim_last = nullptr;   // per k_apply_gain tile: last frame over the limiter's limit, or -1
-    LimState *lim_in = nullptr, *lim_out = nullptr;   // per tile: the limiter state it started from / ended in
+    LimStore lim_in{}, lim_out{};    // per tile: the limiter state it started from / ended in
     int *lim_need = nullptr;         // per tile: its start is not its predecessor's end (yet)
     cudaStream_t stream = nullptr;
 };
@@ -197,6 +197,8 @@ struct ame_plan {
     int *d_peak = nullptr;
     unsigned *d_tp = nullptr;               // per track: float bits of the oversampled peak (k_true_peak)
     bool any_limiter = false, any_tp = false;
+    int lim_keep = 2;                       // queue entries a recorded limiter state holds: look-ahead frames + 2
+    int *d_lim_stats = nullptr;             // open tiles after the limiter's round 0 / 1 / 2, accumulated
     int slot_gain_jobs = 0;
     ame_track_result *d_results = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
@@ -419,7 +421,7 @@ struct Bufs {
     int64_t *hist = nullptr;
     int16_t *norm = nullptr;
     long long *lim_last = nullptr;
-    LimState *lim_in = nullptr, *lim_out = nullptr;
+    LimStore lim_in{}, lim_out{};
     int *lim_need = nullptr;
 };
 
@@ -548,7 +550,8 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
             for (int round = 0; round <= kLimRounds; ++round) {
                 k_limiter<<<w.gain_n, 256, 0, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round);
                 LAUNCH_CHECK(p);
-                k_lim_verify<<<(w.gain_n + 127) / 128, 128, 0, s>>>(gj, w.gain_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need);
+                k_lim_verify<<<(w.gain_n + 3) / 4, 128, 0, s>>>(gj, w.gain_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
+                                                                 p->d_lim_stats + round);
                 LAUNCH_CHECK(p);
             }
             k_lim_fallback<<<w.gain_n, 32, 0, s>>>(gj, w.gain_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need);
@@ -603,13 +606,14 @@ void ame_plan_destroy(ame_plan *p) {
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
                     p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts,
-                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_tp, p->d_results,
+                    p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_tp, p->d_lim_stats, p->d_results,
                     p->d_chain_stats};
     cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
     for (void *q : ptrs) dev_free(q);
     for (Slot &sl : p->slots) {
         for (void *q : {(void *)sl.pre, (void *)sl.bands, (void *)sl.rms, (void *)sl.list, (void *)sl.tile_cnt, (void *)sl.n_flagged,
-                        (void *)sl.grp, (void *)sl.att, (void *)sl.norm, (void *)sl.lim_last, (void *)sl.lim_in, (void *)sl.lim_out,
+                        (void *)sl.grp, (void *)sl.att, (void *)sl.norm, (void *)sl.lim_last, (void *)sl.lim_in.st, (void *)sl.lim_in.qframe,
+                        (void *)sl.lim_in.qdelta, (void *)sl.lim_out.st, (void *)sl.lim_out.qframe, (void *)sl.lim_out.qdelta,
                         (void *)sl.lim_need})
             dev_free(q);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -666,6 +670,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         p->n_sb_total += p->tdev[t].n_sb;
         p->tdev[t].pad = 0;
         p->any_limiter = p->any_limiter || (tp.flags & AME_F_LIMITER);
+        if (tp.flags & AME_F_LIMITER) p->lim_keep = std::max(p->lim_keep, tp.lim_frames + 2);
         p->any_tp = p->any_tp || (tp.flags & AME_F_TRUE_PEAK);
     }
     for (size_t i = 1; i < spans.size(); ++i)
@@ -925,10 +930,15 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         if (p->any_limiter &&
             ((rc = dmalloc(p, (void **)&sl.norm, (size_t)p->slot_frames * 4)) ||
              (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(long long))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_in, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_out, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.st, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.st, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.qframe, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(int))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.qframe, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(int))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.qdelta, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(double))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.qdelta, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(double))) ||
              (rc = dmalloc(p, (void **)&sl.lim_need, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(int)))))
             return bail(rc);
+        sl.lim_in.keep = sl.lim_out.keep = p->lim_keep;
         // the filters read a few frames past a track's end (whole 16 / 32-byte groups, never stored): keep them defined
         if (cudaMemsetAsync(sl.pre, 0, (size_t)p->slot_frames * 4, 0) != cudaSuccess ||
             (p->mb_frames && cudaMemsetAsync(sl.bands, 0, (size_t)p->mb_frames * 12, 0) != cudaSuccess))
@@ -940,8 +950,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         (rc = dmalloc(p, (void **)&p->d_hist_st, (size_t)n_tracks * 1000 * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_peak, (size_t)n_tracks * 4)) ||
         (rc = dmalloc(p, (void **)&p->d_tp, (size_t)n_tracks * 4)) ||
+        (rc = dmalloc(p, (void **)&p->d_lim_stats, 4 * sizeof(int))) ||
         (rc = dmalloc(p, (void **)&p->d_results, (size_t)n_tracks * sizeof(ame_track_result))))
         return bail(rc);
+    if (cudaMemsetAsync(p->d_lim_stats, 0, 4 * sizeof(int), 0) != cudaSuccess) return bail(fail(AME_E_CUDA, "cudaMemset failed"));
     if (cudaMemsetAsync(p->d_chain_stats, 0, std::max<size_t>(chain_jobs.size(), 1) * 2 * sizeof(int), 0) != cudaSuccess)
         return bail(fail(AME_E_CUDA, "cudaMemset failed"));
     if (o.host_io) {
@@ -1050,6 +1062,17 @@ int ame_plan_chain_stats(ame_plan *p, int64_t *n_chains, int64_t *steps, int64_t
     if (max_steps) *max_steps = mx;
     if (passes) *passes = ps;
     if (max_passes) *max_passes = mp;
+    return AME_OK;
+}
+
+int ame_plan_limiter_stats(ame_plan *p, int64_t *open_tiles) {
+    if (!p || !open_tiles) return fail(AME_E_INVALID, "NULL argument");
+    GUARD(p->device);
+    CU(cudaDeviceSynchronize());
+    int h[4] = {0, 0, 0, 0};
+    CU(cudaMemcpy(h, p->d_lim_stats, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(p->d_lim_stats, 0, sizeof h));
+    for (int i = 0; i < 3; ++i) open_tiles[i] = h[i];
     return AME_OK;
 }
 

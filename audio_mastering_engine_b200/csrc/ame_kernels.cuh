@@ -1216,14 +1216,19 @@ k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restric
 // scale / round / store them after.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLimQueue = 1024;     // queue capacity >= B + 2 (B <= 1000 frames is validated by the host)
-constexpr int kLimKeep = 8;         // queue entries a recorded state can hold (more: the state is "not representable")
 
-struct LimState {                   // the machine between two frames
+// The machine between two frames, as recorded per tile.  The queue (one entry per over-limit frame still inside the
+// look-ahead ring: up to B of them while the signal clips) lives in two side arrays of `keep` = B_max + 2 entries per tile.
+struct LimState {
     double att, delta;
-    int qlen;                       // -1: more than kLimKeep entries, cannot be compared / resumed
+    int qlen;
     int exact;                      // as a tile's START state: known to be the true one (initial state / track start)
-    int qframe[kLimKeep];           // frame (relative to the track) of every queued peak, in queue order
-    double qdelta[kLimKeep];
+};
+struct LimStore {                   // where the recorded states of a launch live
+    LimState *st;                   // [tiles]
+    int *qframe;                    // [tiles][keep] frame (relative to the track) of every queued peak, in queue order
+    double *qdelta;                 // [tiles][keep]
+    int keep;
 };
 
 struct LimSmem {
@@ -1241,7 +1246,7 @@ struct LimCtx {
     double limit, level, fsrel;
 };
 
-struct LimRegs { double att, delta; int qiter, qlen; };      // lane 0's part of the machine
+struct LimRegs { double att, delta; int qiter, qlen; };      // the scalar part of the machine, the same in every lane
 
 __device__ __forceinline__ int lim_out_sample(int x, double att, double limit, double level) {
     double v = __dmul_rn((double)x * (1.0 / 32768.0), att);          // buf[c] * att
@@ -1262,35 +1267,57 @@ __device__ __forceinline__ void lim_reset(LimRegs &r, LimSmem &sm, int lane) {
     __syncwarp();
 }
 
-__device__ __forceinline__ void lim_save(const LimRegs &r, const LimSmem &sm, LimState *st, int exact) {   // lane 0
-    st->att = r.att; st->delta = r.delta; st->exact = exact;
-    st->qlen = r.qlen <= kLimKeep ? r.qlen : -1;
-    for (int k = 0; k < kLimKeep; ++k) {
-        const bool in = k < r.qlen;
-        st->qframe[k] = in ? sm.qframe[(r.qiter + k) % kLimQueue] : -1;
-        st->qdelta[k] = in ? sm.qdelta[(r.qiter + k) % kLimQueue] : 0.0;
+__device__ __forceinline__ void lim_save(const LimRegs &r, const LimSmem &sm, const LimStore &S, int tile, int exact, int lane) {
+    if (lane == 0) S.st[tile] = LimState{r.att, r.delta, r.qlen, exact};
+    for (int k = lane; k < r.qlen; k += 32) {
+        S.qframe[(size_t)tile * S.keep + k] = sm.qframe[(r.qiter + k) % kLimQueue];
+        S.qdelta[(size_t)tile * S.keep + k] = sm.qdelta[(r.qiter + k) % kLimQueue];
     }
 }
 
-__device__ __forceinline__ void lim_load(LimRegs &r, LimSmem &sm, const LimState &st, int lane) {   // whole warp; st.qlen >= 0
+__device__ __forceinline__ void lim_load(LimRegs &r, LimSmem &sm, const LimStore &S, int tile, int lane) {
     lim_reset(r, sm, lane);
+    const LimState st = S.st[tile];
     r.att = st.att; r.delta = st.delta; r.qiter = 0; r.qlen = st.qlen;
-    if (lane == 0)
-        for (int k = 0; k < st.qlen; ++k) { sm.qframe[k] = st.qframe[k]; sm.qdelta[k] = st.qdelta[k]; }
+    for (int k = lane; k < st.qlen; k += 32) {
+        sm.qframe[k] = S.qframe[(size_t)tile * S.keep + k];
+        sm.qdelta[k] = S.qdelta[(size_t)tile * S.keep + k];
+    }
     __syncwarp();
 }
 
-__device__ __forceinline__ bool lim_equal(const LimState &a, const LimState &b) {
-    if (a.qlen < 0 || b.qlen < 0 || a.qlen != b.qlen) return false;
-    if (__double_as_longlong(a.att) != __double_as_longlong(b.att) || __double_as_longlong(a.delta) != __double_as_longlong(b.delta)) return false;
-    for (int k = 0; k < a.qlen; ++k)
-        if (a.qframe[k] != b.qframe[k] || __double_as_longlong(a.qdelta[k]) != __double_as_longlong(b.qdelta[k])) return false;
-    return true;
+// recorded state (A, tile a) == recorded state (B, tile b), field by field and bit by bit (whole warp; same result in every lane)
+__device__ __forceinline__ bool lim_equal(const LimStore &A, int a, const LimStore &Bs, int b, int lane) {
+    const LimState x = A.st[a], y = Bs.st[b];
+    bool eq = x.qlen == y.qlen && __double_as_longlong(x.att) == __double_as_longlong(y.att) &&
+              __double_as_longlong(x.delta) == __double_as_longlong(y.delta);
+    if (eq)
+        for (int k = lane; k < x.qlen; k += 32)
+            eq = eq && A.qframe[(size_t)a * A.keep + k] == Bs.qframe[(size_t)b * Bs.keep + k] &&
+                 __double_as_longlong(A.qdelta[(size_t)a * A.keep + k]) == __double_as_longlong(Bs.qdelta[(size_t)b * Bs.keep + k]);
+    return __all_sync(kFull, eq);
 }
 
-// the machine over frames [n_lo, n_hi) of the packed buffer (whole warp); output is stored when `emit`
+// the live machine == recorded state (S, tile)
+__device__ __forceinline__ bool lim_equal_live(const LimRegs &r, const LimSmem &sm, const LimStore &S, int tile, int lane) {
+    const LimState y = S.st[tile];
+    bool eq = r.qlen == y.qlen && __double_as_longlong(r.att) == __double_as_longlong(y.att) &&
+              __double_as_longlong(r.delta) == __double_as_longlong(y.delta);
+    if (eq)
+        for (int k = lane; k < r.qlen; k += 32)
+            eq = eq && sm.qframe[(r.qiter + k) % kLimQueue] == S.qframe[(size_t)tile * S.keep + k] &&
+                 __double_as_longlong(sm.qdelta[(r.qiter + k) % kLimQueue]) == __double_as_longlong(S.qdelta[(size_t)tile * S.keep + k]);
+    return __all_sync(kFull, eq);
+}
+
+// The machine over frames [n_lo, n_hi) of the packed buffer; output is stored when `emit`.  The whole warp runs the
+// frame loop in lockstep with the scalar state replicated in every lane (same inputs, same arithmetic); only the search
+// through the queue when an over-limit frame arrives (af_alimiter.c walks it entry by entry - up to B entries while the
+// signal clips) is spread over the lanes, 32 entries per step.
 __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm, int64_t n_lo, int64_t n_hi, bool emit, int lane) {
     const int bufsize = 2 * c.B;
+    double att = r.att, delta = r.delta;
+    int qiter = r.qiter, qlen = r.qlen;
     for (int64_t n0 = n_lo; n0 < n_hi; n0 += 32) {
         const int64_t n = n0 + lane, m = n - (c.B - 1);
         const uint32_t win = n < n_hi ? __ldg(c.x + n) : 0u;
@@ -1300,63 +1327,75 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
         const unsigned over = __ballot_sync(kFull, n < n_hi && sm.pin[lane] >= c.thr_i);
         __syncwarp();
         const int n_valid = (int)min((int64_t)32, n_hi - n0);
-        if (lane == 0) {
-            double att = r.att, delta = r.delta;
-            int qiter = r.qiter, qlen = r.qlen;
-            if (over == 0 && qlen == 0 && delta == 0.0) {             // nothing can happen in these 32 frames
-                for (int k = 0; k < n_valid; ++k) sm.att[k] = att;
-            } else {
-                for (int k = 0; k < n_valid; ++k) {
-                    const int rel = (int)(n0 + k - c.t_begin);
-                    if (over & (1u << k)) {                           // the entering frame is over the limit
-                        const double peak = (double)sm.pin[k] * (1.0 / 32768.0);
-                        const double patt = fmin(c.limit / peak, 1.0);
-                        const double rdelta = (1.0 - patt) / c.fsrel;
-                        const double d = (c.limit / peak - att) / bufsize * 2;
-                        if (d < delta) {
-                            delta = d;
-                            sm.qframe[0] = rel; sm.qframe[1] = -1; sm.qdelta[0] = rdelta;
-                            qlen = 1; qiter = 0;
-                        } else {
-                            bool found = false;
-                            int i = qiter;
-                            for (; i < qiter + qlen; ++i) {
-                                const int j = i % kLimQueue;
+        if (over == 0 && qlen == 0 && delta == 0.0) {                 // nothing can happen in these 32 frames
+            if (lane < n_valid) sm.att[lane] = att;
+        } else {
+            for (int k = 0; k < n_valid; ++k) {
+                const int rel = (int)(n0 + k - c.t_begin);
+                if (over & (1u << k)) {                               // the entering frame is over the limit
+                    const double peak = (double)sm.pin[k] * (1.0 / 32768.0);
+                    const double patt = fmin(c.limit / peak, 1.0);
+                    const double rdelta = (1.0 - patt) / c.fsrel;
+                    const double d = (c.limit / peak - att) / bufsize * 2;
+                    if (d < delta) {
+                        delta = d;
+                        if (lane == 0) { sm.qframe[0] = rel; sm.qframe[1] = -1; sm.qdelta[0] = rdelta; }
+                        qlen = 1; qiter = 0;
+                    } else {
+                        int found = -1;                               // first queue position whose slope the new peak undercuts
+                        for (int i0 = 0; i0 < qlen && found < 0; i0 += 32) {
+                            const int i = i0 + lane;
+                            bool hit = false;
+                            double pdelta = 0.0;
+                            if (i < qlen) {
+                                const int j = (qiter + i) % kLimQueue;
                                 const uint32_t w = __ldg(c.x + c.t_begin + sm.qframe[j]);
                                 const double ppeak = (double)max(abs((int)(int16_t)(w & 0xffffu)), abs((int)(int16_t)(w >> 16))) * (1.0 / 32768.0);
-                                const double pdelta = (c.limit / peak - c.limit / ppeak) / (double)(rel - sm.qframe[j]);
-                                if (pdelta < sm.qdelta[j]) { sm.qdelta[j] = pdelta; found = true; break; }
+                                pdelta = (c.limit / peak - c.limit / ppeak) / (double)(rel - sm.qframe[j]);
+                                hit = pdelta < sm.qdelta[j];
                             }
-                            if (found) {
-                                qlen = i - qiter + 1;
+                            const unsigned hits = __ballot_sync(kFull, hit);
+                            if (hits) {
+                                const int first = __ffs(hits) - 1;
+                                found = i0 + first;
+                                const double pd = __shfl_sync(kFull, pdelta, first);
+                                if (lane == 0) sm.qdelta[(qiter + found) % kLimQueue] = pd;
+                            }
+                        }
+                        if (found >= 0) {
+                            qlen = found + 1;
+                            if (lane == 0) {
                                 sm.qframe[(qiter + qlen) % kLimQueue] = rel;
                                 sm.qdelta[(qiter + qlen) % kLimQueue] = rdelta;
                                 sm.qframe[(qiter + qlen + 1) % kLimQueue] = -1;
-                                ++qlen;
                             }
+                            ++qlen;
                         }
                     }
-                    att += delta;
-                    sm.att[k] = att;                                  // the leaving frame is scaled by this
-                    if (rel >= c.B - 1 && rel - (c.B - 1) == sm.qframe[qiter]) {   // a queued peak leaves the ring
-                        delta = sm.qdelta[qiter];
-                        att = c.limit / ((double)sm.pout[k] * (1.0 / 32768.0));
-                        --qlen;
-                        sm.qframe[qiter] = -1;
-                        qiter = (qiter + 1) % kLimQueue;
-                    }
-                    if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; sm.qframe[0] = -1; }
-                    if (att <= 0.0) { att = 0.0000000000001; delta = (1.0 - att) / c.fsrel; }
-                    if (att != 1.0 && (1.0 - att) < 0.0000000000001) att = 1.0;
-                    if (delta != 0.0 && fabs(delta) < 0.00000000000001) delta = 0.0;
+                    __syncwarp();
                 }
+                att += delta;
+                if (lane == 0) sm.att[k] = att;                       // the leaving frame is scaled by this
+                if (rel >= c.B - 1 && rel - (c.B - 1) == sm.qframe[qiter]) {   // a queued peak leaves the ring
+                    delta = sm.qdelta[qiter];
+                    att = c.limit / ((double)sm.pout[k] * (1.0 / 32768.0));
+                    --qlen;
+                    __syncwarp();
+                    if (lane == 0) sm.qframe[qiter] = -1;
+                    qiter = (qiter + 1) % kLimQueue;
+                    __syncwarp();
+                }
+                if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; __syncwarp(); if (lane == 0) sm.qframe[0] = -1; __syncwarp(); }
+                if (att <= 0.0) { att = 0.0000000000001; delta = (1.0 - att) / c.fsrel; }
+                if (att != 1.0 && (1.0 - att) < 0.0000000000001) att = 1.0;
+                if (delta != 0.0 && fabs(delta) < 0.00000000000001) delta = 0.0;
             }
-            r.att = att; r.delta = delta; r.qiter = qiter; r.qlen = qlen;
         }
         __syncwarp();
         if (emit && lane < n_valid) lim_emit(c, n, sm.att[lane]);
         __syncwarp();
     }
+    r.att = att; r.delta = delta; r.qiter = qiter; r.qlen = qlen;
 }
 
 struct LimTile { bool limiter, first, quiet_start, simple; int64_t G; };
@@ -1389,7 +1428,7 @@ __device__ __forceinline__ LimCtx lim_ctx(const ame_track_params *tp, const int1
 __global__ void __launch_bounds__(256)
 k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restrict__ lim_last,
           const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ norm, int16_t *__restrict__ out,
-          LimState *__restrict__ st_in, LimState *__restrict__ st_out, int *__restrict__ need, int round) {
+          LimStore IN, LimStore OUT, int *__restrict__ need, int round) {
     __shared__ LimSmem sm;
     const int tile = blockIdx.x;
     const GainJob job = jobs[tile];
@@ -1403,10 +1442,9 @@ k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restr
         if (t.simple) {                                               // initial state throughout: elementwise
             for (int64_t n = job.begin + threadIdx.x; n < job.end; n += blockDim.x) lim_emit(c, n, 1.0);
             if (threadIdx.x == 0) {
-                LimState z;
-                z.att = 1.0; z.delta = 0.0; z.qlen = 0; z.exact = 1;
-                for (int k = 0; k < kLimKeep; ++k) { z.qframe[k] = -1; z.qdelta[k] = 0.0; }
-                st_in[tile] = z; st_out[tile] = z; need[tile] = 0;
+                IN.st[tile] = LimState{1.0, 0.0, 0, 1};
+                OUT.st[tile] = LimState{1.0, 0.0, 0, 0};
+                need[tile] = 0;
             }
             return;
         }
@@ -1418,41 +1456,41 @@ k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restr
             exact = ws == c.t_begin;                                  // from the track start it is no guess
             lim_run(c, r, sm, ws, job.begin, false, lane);
         }
-        if (lane == 0) lim_save(r, sm, st_in + tile, exact);
+        lim_save(r, sm, IN, tile, exact, lane);
     } else {
         // open, and the predecessor is settled (it does not run in this round, so its recorded end is stable)
         if (threadIdx.x >= 32 || !need[tile] || need[tile - 1]) return;
-        const LimState pred = st_out[tile - 1];
-        if (pred.qlen < 0) return;                                    // k_lim_fallback's case
-        lim_load(r, sm, pred, lane);
-        if (lane == 0) { LimState s0 = pred; s0.exact = 0; st_in[tile] = s0; }
+        lim_load(r, sm, OUT, tile - 1, lane);
+        lim_save(r, sm, IN, tile, 0, lane);
     }
     lim_run(c, r, sm, job.begin, job.end, true, lane);
-    if (lane == 0) lim_save(r, sm, st_out + tile, 0);
+    lim_save(r, sm, OUT, tile, 0, lane);
 }
 
-// does every tile start where its predecessor ended?
-__global__ void k_lim_verify(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
-                             const LimState *__restrict__ st_in, const LimState *__restrict__ st_out, int *__restrict__ need) {
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+// does every tile start where its predecessor ended?  One warp per tile; counts the open tiles of this pass.
+__global__ void __launch_bounds__(128)
+k_lim_verify(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
+             LimStore IN, LimStore OUT, int *__restrict__ need, int *__restrict__ open_count) {
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (tile >= n_jobs) return;
     const GainJob job = jobs[tile];
     int open = 0;
-    if ((tracks[job.track].flags & AME_F_LIMITER) && tile > 0 && jobs[tile - 1].track == job.track && !st_in[tile].exact)
-        open = !lim_equal(st_in[tile], st_out[tile - 1]);
-    need[tile] = open;
+    if ((tracks[job.track].flags & AME_F_LIMITER) && tile > 0 && jobs[tile - 1].track == job.track && !IN.st[tile].exact)
+        open = !lim_equal(IN, tile, OUT, tile - 1, lane);
+    if (lane == 0) {
+        need[tile] = open;
+        if (open) atomicAdd(open_count, 1);
+    }
 }
 
 // what the repair rounds left open: ONE warp per track walks its tiles in order; at an open tile it resumes from the
-// predecessor's end (or, if that state is not representable, silently from the last tile with an exact start) and keeps
-// walking until its live state equals the recorded start of a tile that is not open - from there on the recorded tiles
-// are the sequential run again
+// predecessor's end and keeps walking until its live state equals the recorded start of a tile that is not open -
+// from there on the recorded tiles are the sequential run again
 __global__ void __launch_bounds__(32)
 k_lim_fallback(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
-               const int16_t *__restrict__ norm, int16_t *__restrict__ out, LimState *__restrict__ st_in,
-               LimState *__restrict__ st_out, const int *__restrict__ need) {
+               const int16_t *__restrict__ norm, int16_t *__restrict__ out, LimStore IN, LimStore OUT,
+               const int *__restrict__ need) {
     __shared__ LimSmem sm;
-    __shared__ LimState live;
     const int first_tile = blockIdx.x;
     const int track = jobs[first_tile].track;
     if (first_tile > 0 && jobs[first_tile - 1].track == track) return;       // not the first tile of its track
@@ -1465,23 +1503,14 @@ k_lim_fallback(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_par
     for (int tile = first_tile; tile < n_jobs && jobs[tile].track == track; ++tile) {
         if (!walking) {
             if (!need[tile]) continue;
-            const LimState pred = st_out[tile - 1];                           // an open tile has a predecessor in its track
-            if (pred.qlen >= 0) {
-                lim_load(r, sm, pred, lane);
-            } else {
-                int j = tile - 1;
-                while (!st_in[j].exact) --j;                                  // the first tile of a track is exact
-                const LimState s0 = st_in[j];
-                lim_load(r, sm, s0, lane);
-                lim_run(c, r, sm, jobs[j].begin, jobs[tile].begin, false, lane);
-            }
+            lim_load(r, sm, OUT, tile - 1, lane);                             // an open tile has a predecessor in its track
             walking = true;
         }
         lim_run(c, r, sm, jobs[tile].begin, jobs[tile].end, true, lane);
-        if (lane == 0) { lim_save(r, sm, st_out + tile, 0); lim_save(r, sm, &live, 0); }
+        lim_save(r, sm, OUT, tile, 0, lane);
         __syncwarp();
         const int next = tile + 1;
-        if (next < n_jobs && jobs[next].track == track && !need[next] && (st_in[next].exact || lim_equal(live, st_in[next])))
+        if (next < n_jobs && jobs[next].track == track && !need[next] && (IN.st[next].exact || lim_equal_live(r, sm, IN, next, lane)))
             walking = false;
     }
 }

@@ -142,6 +142,12 @@ class MasterPlan:
     def n_slots(self):
         return int(self.lib.ame_plan_slot_count(self.handle))
 
+    def limiter_stats(self):
+        """Limiter tiles whose guessed start state was wrong after round 0 / 1 / 2, since the last query."""
+        v = (C.c_int64 * 3)()
+        L.check(self.lib.ame_plan_limiter_stats(self.handle, v))
+        return [int(x) for x in v]
+
     def chain_stats(self):
         """Compressor recurrence of the last call: chains, flagged steps (total, longest chain), passes (total, max)."""
         v = [C.c_int64() for _ in range(4)]

@@ -323,6 +323,11 @@ def run_b200(args, rank, world, local_rank):
     value = audio_total * args.steps / (ms_max * 1e-3)
     infos = plan.master_device(d_in, d_out, stream=stream)             # one more pass, fetching the loudness results
     chain_stats = plan.chain_stats()
+    if args.limiter:
+        plan.limiter_stats()
+        plan.master_device(d_in, d_out, stream=stream, fetch_results=False)
+        chain_stats["limiter_open_tiles_after_round_0_1_2"] = plan.limiter_stats()
+        chain_stats["limiter_tiles"] = n_tr * (-(-n // 32768))
     workspace_gb = round(plan.workspace_bytes / 1e9, 2)
     plan_slots, plan_waves, stride = plan.n_slots, plan.n_waves, plan.total_frames // n_tr
     plan.close()

@@ -175,6 +175,9 @@ int32_t ame_plan_wave_count(const ame_plan *plan);
 int32_t ame_plan_slot_count(const ame_plan *plan);
 /* statistics of the compressor recurrence of the last call (benchmarks): chains, flagged steps in total and in the
  * longest chain, passes (1 + repairs) in total and at most */
+/* limiter (AME_F_LIMITER): tiles whose guessed start state was not their predecessor's end state after round 0, 1, 2
+ * of k_limiter, summed over the calls since the last query (what is open after round 2 is walked sequentially) */
+int ame_plan_limiter_stats(ame_plan *plan, int64_t *open_tiles /* [3] */);
 int ame_plan_chain_stats(ame_plan *plan, int64_t *n_chains, int64_t *steps, int64_t *max_steps, int64_t *passes,
                          int32_t *max_passes);
 
