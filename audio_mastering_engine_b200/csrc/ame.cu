@@ -547,14 +547,21 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
             t_begin(p, S_LIM, s);
             const GainJob *gj = p->d_gain_jobs + w.gain_lo;
             constexpr int kLimRounds = 2;                 // repair rounds before the sequential fallback
+            int cap = 64;
+            while (cap < p->lim_keep + 2) cap *= 2;       // queue capacity in shared memory: a power of two
+            const size_t smem = lim_smem_bytes(cap);
             for (int round = 0; round <= kLimRounds; ++round) {
-                k_limiter<<<w.gain_n, 256, 0, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round);
+                if (round == 0) {                         // the elementwise tiles, 256 threads each
+                    k_limiter<<<w.gain_n, 256, smem, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, 0, cap);
+                    LAUNCH_CHECK(p);
+                }
+                k_limiter<<<w.gain_n, 32, smem, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round, cap);
                 LAUNCH_CHECK(p);
                 k_lim_verify<<<(w.gain_n + 3) / 4, 128, 0, s>>>(gj, w.gain_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
                                                                  p->d_lim_stats + round);
                 LAUNCH_CHECK(p);
             }
-            k_lim_fallback<<<w.gain_n, 32, 0, s>>>(gj, w.gain_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need);
+            k_lim_fallback<<<w.gain_n, 32, smem, s>>>(gj, w.gain_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, cap);
             LAUNCH_CHECK(p);
             t_end(p, S_LIM, s);
         }

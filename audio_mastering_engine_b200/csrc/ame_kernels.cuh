@@ -1215,7 +1215,7 @@ k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restric
 // One warp per non-elementwise tile: lane 0 walks the state 32 frames at a time, all lanes load the frames before and
 // scale / round / store them after.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLimQueue = 1024;     // queue capacity >= B + 2 (B <= 1000 frames is validated by the host)
+constexpr int kLimQueue = 1024;     // largest queue capacity (look-ahead B <= 1000 frames is validated by the host)
 
 // The machine between two frames, as recorded per tile.  The queue (one entry per over-limit frame still inside the
 // look-ahead ring: up to B of them while the signal clips) lives in two side arrays of `keep` = B_max + 2 entries per tile.
@@ -1231,12 +1231,24 @@ struct LimStore {                   // where the recorded states of a launch liv
     int keep;
 };
 
-struct LimSmem {
-    int qframe[kLimQueue];          // -1 = none (the sentinel af_alimiter.c keeps behind the last entry)
-    double qdelta[kLimQueue];
-    double att[32];
-    int pin[32], pout[32];          // peak (max |s16|) of the frame entering / leaving the ring at each of 32 steps
+struct LimSmem {                    // views into the CTA's dynamic shared memory (lim_smem)
+    double *qdelta;                 // [cap]
+    double *att;                    // [32]
+    int *qframe;                    // [cap]  -1 = none (the sentinel af_alimiter.c keeps behind the last entry)
+    int *pin, *pout;                // [32] peak (max |s16|) of the frame entering / leaving the ring at each of 32 steps
+    int mask;                       // cap - 1, cap = a power of two >= look-ahead frames + 4
 };
+__host__ __device__ inline size_t lim_smem_bytes(int cap) { return (size_t)cap * 12 + 32 * 16; }
+__device__ __forceinline__ LimSmem lim_smem(unsigned char *raw, int cap) {
+    LimSmem sm;
+    sm.qdelta = reinterpret_cast<double *>(raw);
+    sm.att = sm.qdelta + cap;
+    sm.qframe = reinterpret_cast<int *>(sm.att + 32);
+    sm.pin = sm.qframe + cap;
+    sm.pout = sm.pin + 32;
+    sm.mask = cap - 1;
+    return sm;
+}
 
 struct LimCtx {
     const uint32_t *x;              // normalised signal (packed buffer)
@@ -1262,7 +1274,7 @@ __device__ __forceinline__ void lim_emit(const LimCtx &c, int64_t n, double att)
 }
 
 __device__ __forceinline__ void lim_reset(LimRegs &r, LimSmem &sm, int lane) {
-    for (int i = lane; i < kLimQueue; i += 32) { sm.qframe[i] = -1; sm.qdelta[i] = 0.0; }
+    for (int i = lane; i <= sm.mask; i += 32) { sm.qframe[i] = -1; sm.qdelta[i] = 0.0; }
     r.att = 1.0; r.delta = 0.0; r.qiter = 0; r.qlen = 0;
     __syncwarp();
 }
@@ -1270,8 +1282,8 @@ __device__ __forceinline__ void lim_reset(LimRegs &r, LimSmem &sm, int lane) {
 __device__ __forceinline__ void lim_save(const LimRegs &r, const LimSmem &sm, const LimStore &S, int tile, int exact, int lane) {
     if (lane == 0) S.st[tile] = LimState{r.att, r.delta, r.qlen, exact};
     for (int k = lane; k < r.qlen; k += 32) {
-        S.qframe[(size_t)tile * S.keep + k] = sm.qframe[(r.qiter + k) % kLimQueue];
-        S.qdelta[(size_t)tile * S.keep + k] = sm.qdelta[(r.qiter + k) % kLimQueue];
+        S.qframe[(size_t)tile * S.keep + k] = sm.qframe[(r.qiter + k) & sm.mask];
+        S.qdelta[(size_t)tile * S.keep + k] = sm.qdelta[(r.qiter + k) & sm.mask];
     }
 }
 
@@ -1305,8 +1317,8 @@ __device__ __forceinline__ bool lim_equal_live(const LimRegs &r, const LimSmem &
               __double_as_longlong(r.delta) == __double_as_longlong(y.delta);
     if (eq)
         for (int k = lane; k < r.qlen; k += 32)
-            eq = eq && sm.qframe[(r.qiter + k) % kLimQueue] == S.qframe[(size_t)tile * S.keep + k] &&
-                 __double_as_longlong(sm.qdelta[(r.qiter + k) % kLimQueue]) == __double_as_longlong(S.qdelta[(size_t)tile * S.keep + k]);
+            eq = eq && sm.qframe[(r.qiter + k) & sm.mask] == S.qframe[(size_t)tile * S.keep + k] &&
+                 __double_as_longlong(sm.qdelta[(r.qiter + k) & sm.mask]) == __double_as_longlong(S.qdelta[(size_t)tile * S.keep + k]);
     return __all_sync(kFull, eq);
 }
 
@@ -1348,7 +1360,7 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                             bool hit = false;
                             double pdelta = 0.0;
                             if (i < qlen) {
-                                const int j = (qiter + i) % kLimQueue;
+                                const int j = (qiter + i) & sm.mask;
                                 const uint32_t w = __ldg(c.x + c.t_begin + sm.qframe[j]);
                                 const double ppeak = (double)max(abs((int)(int16_t)(w & 0xffffu)), abs((int)(int16_t)(w >> 16))) * (1.0 / 32768.0);
                                 pdelta = (c.limit / peak - c.limit / ppeak) / (double)(rel - sm.qframe[j]);
@@ -1359,15 +1371,15 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                                 const int first = __ffs(hits) - 1;
                                 found = i0 + first;
                                 const double pd = __shfl_sync(kFull, pdelta, first);
-                                if (lane == 0) sm.qdelta[(qiter + found) % kLimQueue] = pd;
+                                if (lane == 0) sm.qdelta[(qiter + found) & sm.mask] = pd;
                             }
                         }
                         if (found >= 0) {
                             qlen = found + 1;
                             if (lane == 0) {
-                                sm.qframe[(qiter + qlen) % kLimQueue] = rel;
-                                sm.qdelta[(qiter + qlen) % kLimQueue] = rdelta;
-                                sm.qframe[(qiter + qlen + 1) % kLimQueue] = -1;
+                                sm.qframe[(qiter + qlen) & sm.mask] = rel;
+                                sm.qdelta[(qiter + qlen) & sm.mask] = rdelta;
+                                sm.qframe[(qiter + qlen + 1) & sm.mask] = -1;
                             }
                             ++qlen;
                         }
@@ -1382,7 +1394,7 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                     --qlen;
                     __syncwarp();
                     if (lane == 0) sm.qframe[qiter] = -1;
-                    qiter = (qiter + 1) % kLimQueue;
+                    qiter = (qiter + 1) & sm.mask;
                     __syncwarp();
                 }
                 if (att > 1.0) { att = 1.0; delta = 0.0; qiter = 0; qlen = 0; __syncwarp(); if (lane == 0) sm.qframe[0] = -1; __syncwarp(); }
@@ -1428,13 +1440,17 @@ __device__ __forceinline__ LimCtx lim_ctx(const ame_track_params *tp, const int1
 __global__ void __launch_bounds__(256)
 k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restrict__ lim_last,
           const ame_track_params *__restrict__ tracks, const int16_t *__restrict__ norm, int16_t *__restrict__ out,
-          LimStore IN, LimStore OUT, int *__restrict__ need, int round) {
-    __shared__ LimSmem sm;
+          LimStore IN, LimStore OUT, int *__restrict__ need, int round, int cap) {
+    // round 0 is launched twice: 256 threads per tile for the elementwise tiles (the others leave at once) and ONE warp
+    // per tile for the sequential ones (so that a few thousand of them are resident at a time)
+    extern __shared__ __align__(16) unsigned char lim_raw[];
+    LimSmem sm = lim_smem(lim_raw, cap);
     const int tile = blockIdx.x;
     const GainJob job = jobs[tile];
     const ame_track_params *tp = tracks + job.track;
     const LimTile t = lim_classify(jobs, tile, lim_last, tp);
     if (!t.limiter) { if (round == 0 && threadIdx.x == 0) need[tile] = 0; return; }
+    if (round == 0 && t.simple != (blockDim.x > 32)) return;
     const LimCtx c = lim_ctx(tp, norm, out);
     const int lane = threadIdx.x & 31;
     LimRegs r;
@@ -1448,7 +1464,6 @@ k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restr
             }
             return;
         }
-        if (threadIdx.x >= 32) return;
         lim_reset(r, sm, lane);
         int exact = 1;
         if (!t.quiet_start) {                                         // guess: the machine over the 2 G frames in front
@@ -1459,7 +1474,7 @@ k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restr
         lim_save(r, sm, IN, tile, exact, lane);
     } else {
         // open, and the predecessor is settled (it does not run in this round, so its recorded end is stable)
-        if (threadIdx.x >= 32 || !need[tile] || need[tile - 1]) return;
+        if (!need[tile] || need[tile - 1]) return;
         lim_load(r, sm, OUT, tile - 1, lane);
         lim_save(r, sm, IN, tile, 0, lane);
     }
@@ -1489,8 +1504,9 @@ k_lim_verify(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_param
 __global__ void __launch_bounds__(32)
 k_lim_fallback(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,
                const int16_t *__restrict__ norm, int16_t *__restrict__ out, LimStore IN, LimStore OUT,
-               const int *__restrict__ need) {
-    __shared__ LimSmem sm;
+               const int *__restrict__ need, int cap) {
+    extern __shared__ __align__(16) unsigned char lim_raw[];
+    LimSmem sm = lim_smem(lim_raw, cap);
     const int first_tile = blockIdx.x;
     const int track = jobs[first_tile].track;
     if (first_tile > 0 && jobs[first_tile - 1].track == track) return;       // not the first tile of its track
