@@ -1233,16 +1233,18 @@ struct LimStore {                   // where the recorded states of a launch liv
 
 struct LimSmem {                    // views into the CTA's dynamic shared memory (lim_smem)
     double *qdelta;                 // [cap]
+    double *qratio;                 // [cap]  limit / peak of the queued frame (af_alimiter.c recomputes it from the ring at every search)
     double *att;                    // [32]
     int *qframe;                    // [cap]  -1 = none (the sentinel af_alimiter.c keeps behind the last entry)
     int *pin, *pout;                // [32] peak (max |s16|) of the frame entering / leaving the ring at each of 32 steps
     int mask;                       // cap - 1, cap = a power of two >= look-ahead frames + 4
 };
-__host__ __device__ inline size_t lim_smem_bytes(int cap) { return (size_t)cap * 12 + 32 * 16; }
+__host__ __device__ inline size_t lim_smem_bytes(int cap) { return (size_t)cap * 20 + 32 * 16; }
 __device__ __forceinline__ LimSmem lim_smem(unsigned char *raw, int cap) {
     LimSmem sm;
     sm.qdelta = reinterpret_cast<double *>(raw);
-    sm.att = sm.qdelta + cap;
+    sm.qratio = sm.qdelta + cap;
+    sm.att = sm.qratio + cap;
     sm.qframe = reinterpret_cast<int *>(sm.att + 32);
     sm.pin = sm.qframe + cap;
     sm.pout = sm.pin + 32;
@@ -1298,6 +1300,16 @@ __device__ __forceinline__ void lim_load(LimRegs &r, LimSmem &sm, const LimStore
     __syncwarp();
 }
 
+// limit / peak of every queued frame, from the signal (after a load; the machine keeps them current itself)
+__device__ __forceinline__ void lim_ratios(const LimCtx &c, const LimRegs &r, LimSmem &sm, int lane) {
+    for (int k = lane; k < r.qlen; k += 32) {
+        const int j = (r.qiter + k) & sm.mask;
+        const uint32_t w = __ldg(c.x + c.t_begin + sm.qframe[j]);
+        sm.qratio[j] = c.limit / ((double)max(abs((int)(int16_t)(w & 0xffffu)), abs((int)(int16_t)(w >> 16))) * (1.0 / 32768.0));
+    }
+    __syncwarp();
+}
+
 // recorded state (A, tile a) == recorded state (B, tile b), field by field and bit by bit (whole warp; same result in every lane)
 __device__ __forceinline__ bool lim_equal(const LimStore &A, int a, const LimStore &Bs, int b, int lane) {
     const LimState x = A.st[a], y = Bs.st[b];
@@ -1348,10 +1360,11 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                     const double peak = (double)sm.pin[k] * (1.0 / 32768.0);
                     const double patt = fmin(c.limit / peak, 1.0);
                     const double rdelta = (1.0 - patt) / c.fsrel;
-                    const double d = (c.limit / peak - att) / bufsize * 2;
+                    const double ratio = c.limit / peak;
+                    const double d = (ratio - att) / bufsize * 2;
                     if (d < delta) {
                         delta = d;
-                        if (lane == 0) { sm.qframe[0] = rel; sm.qframe[1] = -1; sm.qdelta[0] = rdelta; }
+                        if (lane == 0) { sm.qframe[0] = rel; sm.qframe[1] = -1; sm.qdelta[0] = rdelta; sm.qratio[0] = ratio; }
                         qlen = 1; qiter = 0;
                     } else {
                         int found = -1;                               // first queue position whose slope the new peak undercuts
@@ -1361,9 +1374,7 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                             double pdelta = 0.0;
                             if (i < qlen) {
                                 const int j = (qiter + i) & sm.mask;
-                                const uint32_t w = __ldg(c.x + c.t_begin + sm.qframe[j]);
-                                const double ppeak = (double)max(abs((int)(int16_t)(w & 0xffffu)), abs((int)(int16_t)(w >> 16))) * (1.0 / 32768.0);
-                                pdelta = (c.limit / peak - c.limit / ppeak) / (double)(rel - sm.qframe[j]);
+                                pdelta = (ratio - sm.qratio[j]) / (double)(rel - sm.qframe[j]);     // (limit/peak - limit/ppeak) / distance
                                 hit = pdelta < sm.qdelta[j];
                             }
                             const unsigned hits = __ballot_sync(kFull, hit);
@@ -1379,6 +1390,7 @@ __device__ __forceinline__ void lim_run(const LimCtx &c, LimRegs &r, LimSmem &sm
                             if (lane == 0) {
                                 sm.qframe[(qiter + qlen) & sm.mask] = rel;
                                 sm.qdelta[(qiter + qlen) & sm.mask] = rdelta;
+                                sm.qratio[(qiter + qlen) & sm.mask] = ratio;
                                 sm.qframe[(qiter + qlen + 1) & sm.mask] = -1;
                             }
                             ++qlen;
@@ -1476,6 +1488,7 @@ k_limiter(const GainJob *__restrict__ jobs, int n_jobs, const long long *__restr
         // open, and the predecessor is settled (it does not run in this round, so its recorded end is stable)
         if (!need[tile] || need[tile - 1]) return;
         lim_load(r, sm, OUT, tile - 1, lane);
+        lim_ratios(c, r, sm, lane);
         lim_save(r, sm, IN, tile, 0, lane);
     }
     lim_run(c, r, sm, job.begin, job.end, true, lane);
@@ -1520,6 +1533,7 @@ k_lim_fallback(const GainJob *__restrict__ jobs, int n_jobs, const ame_track_par
         if (!walking) {
             if (!need[tile]) continue;
             lim_load(r, sm, OUT, tile - 1, lane);                             // an open tile has a predecessor in its track
+            lim_ratios(c, r, sm, lane);
             walking = true;
         }
         lim_run(c, r, sm, jobs[tile].begin, jobs[tile].end, true, lane);
