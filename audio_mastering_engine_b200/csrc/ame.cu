@@ -113,6 +113,7 @@ int upload(T **dptr, const std::vector<T> &v) {
     return AME_OK;
 }
 
+constexpr int kLimMaxTile = 1 << 20;     // longest limiter tile (look-ahead + release of the slowest setting must fit one)
 constexpr int kMaxTimedSteps = 8;
 constexpr int kMaxTimedWaves = 128;
 constexpr int kTimedSlots = kMaxTimedWaves * AME_N_KERNELS;   // per step
@@ -127,7 +128,7 @@ struct Wave {
     int track_lo = 0, track_hi = 0;
     int64_t frame_lo = 0, frame_hi = 0;            // packed-buffer range (multiples of 8 frames)
     int eq_lo = 0, eq_n = 0, split_lo = 0, split_n = 0, chain_lo = 0, chain_n = 0, wf_lo = 0, wf_n = 0;
-    int chunk_lo = 0, chunk_n = 0, kw_lo = 0, kw_n = 0, gain_lo = 0, gain_n = 0;
+    int chunk_lo = 0, chunk_n = 0, kw_lo = 0, kw_n = 0, gain_lo = 0, gain_n = 0, lim_lo = 0, lim_n = 0;
     int64_t seg_lo = 0, seg_hi = 0;
     int slot = 0;                                  // workspace slot (and stream) this wave runs in
     bool limiter = false;                          // a track of the wave has the limiter stage
@@ -184,7 +185,7 @@ struct ame_plan {
     WfJob *d_wf_jobs = nullptr;
     MbChunk *d_mb_chunks = nullptr;
     KwJob *d_kw_jobs = nullptr;
-    GainJob *d_gain_jobs = nullptr;
+    GainJob *d_gain_jobs = nullptr, *d_lim_jobs = nullptr;   // limiter tiles: the same (begin, end, track) records, shorter tiles
     AttEntry *d_tables = nullptr;
     double *d_luts = nullptr;
     int n_luts = 0;
@@ -199,7 +200,7 @@ struct ame_plan {
     bool any_limiter = false, any_tp = false;
     int lim_keep = 2;                       // queue entries a recorded limiter state holds: look-ahead frames + 2
     int *d_lim_stats = nullptr;             // open tiles after the limiter's round 0 / 1 / 2, accumulated
-    int slot_gain_jobs = 0;
+    int slot_lim_jobs = 0;
     ame_track_result *d_results = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;                       // host path: copy-in / copy-out
     std::vector<cudaEvent_t> ev_in, ev_run;                             // per wave
@@ -333,7 +334,7 @@ int validate(const ame_track_params &t, int idx) {
             return fail(AME_E_UNSUPPORTED, "track %d: the limiter is one sequential state machine over the whole track and cannot "
                                            "run on a time shard; limit the gathered output instead", idx);
         if (t.lim_frames < 1 || t.lim_frames > kLimQueue - 24 || !(t.lim_limit > 0.0 && t.lim_limit <= 1.0) || !(t.lim_fs_release > 0.0) ||
-            t.lim_release_frames < 1 || t.lim_frames + t.lim_release_frames + 8 > kGainTile || t.lim_thr_i < 1)
+            t.lim_release_frames < 1 || t.lim_frames + t.lim_release_frames + 8 > kLimMaxTile || t.lim_thr_i < 1)
             return fail(AME_E_INVALID, "track %d: bad limiter parameters (look-ahead %d frames, release %d frames)", idx, t.lim_frames,
                         t.lim_release_frames);
     }
@@ -540,28 +541,29 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
     t_end(p, S_FIN, s);
     if (w.gain_n) {
         t_begin(p, S_GAIN, s);
-        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, p->d_tracks, d_pre, d_out, d_norm, lim_last);
+        if (w.limiter) CU(cudaMemsetAsync(lim_last, 0xff, (size_t)w.lim_n * sizeof(long long), s));      // -1: no frame over the limit
+        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, p->d_tracks, p->d_tdev, d_pre, d_out, d_norm, lim_last);
         LAUNCH_CHECK(p);
         t_end(p, S_GAIN, s);
         if (w.limiter) {
             t_begin(p, S_LIM, s);
-            const GainJob *gj = p->d_gain_jobs + w.gain_lo;
+            const GainJob *gj = p->d_lim_jobs + w.lim_lo;
             constexpr int kLimRounds = 2;                 // repair rounds before the sequential fallback
             int cap = 64;
             while (cap < p->lim_keep + 2) cap *= 2;       // queue capacity in shared memory: a power of two
             const size_t smem = lim_smem_bytes(cap);
             for (int round = 0; round <= kLimRounds; ++round) {
                 if (round == 0) {                         // the elementwise tiles, 256 threads each
-                    k_limiter<<<w.gain_n, 256, smem, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, 0, cap);
+                    k_limiter<<<w.lim_n, 256, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, 0, cap);
                     LAUNCH_CHECK(p);
                 }
-                k_limiter<<<w.gain_n, 32, smem, s>>>(gj, w.gain_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round, cap);
+                k_limiter<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round, cap);
                 LAUNCH_CHECK(p);
-                k_lim_verify<<<(w.gain_n + 3) / 4, 128, 0, s>>>(gj, w.gain_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
+                k_lim_verify<<<(w.lim_n + 3) / 4, 128, 0, s>>>(gj, w.lim_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
                                                                  p->d_lim_stats + round);
                 LAUNCH_CHECK(p);
             }
-            k_lim_fallback<<<w.gain_n, 32, smem, s>>>(gj, w.gain_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, cap);
+            k_lim_fallback<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, cap);
             LAUNCH_CHECK(p);
             t_end(p, S_LIM, s);
         }
@@ -612,7 +614,7 @@ void ame_plan_destroy(ame_plan *p) {
     if (!p) return;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->d_tracks, p->d_tdev, p->d_mb_delta, p->d_eq_jobs, p->d_split_jobs, p->d_wf_jobs, p->d_mb_chunks,
-                    p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_tables, p->d_luts,
+                    p->d_chain_jobs, p->d_kw_jobs, p->d_gain_jobs, p->d_lim_jobs, p->d_tables, p->d_luts,
                     p->d_in, p->d_out, p->d_energy, p->d_hist, p->d_hist_st, p->d_peak, p->d_tp, p->d_lim_stats, p->d_results,
                     p->d_chain_stats};
     cudaDeviceSynchronize();            // nothing of this plan may still be running when its memory goes back to the pool
@@ -676,6 +678,8 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         p->tdev[t].sb_offset = p->n_sb_total;
         p->n_sb_total += p->tdev[t].n_sb;
         p->tdev[t].pad = 0;
+        p->tdev[t].lim_tile0 = 0;
+        p->tdev[t].lim_shift = 15;
         p->any_limiter = p->any_limiter || (tp.flags & AME_F_LIMITER);
         if (tp.flags & AME_F_LIMITER) p->lim_keep = std::max(p->lim_keep, tp.lim_frames + 2);
         p->any_tp = p->any_tp || (tp.flags & AME_F_TRUE_PEAK);
@@ -792,7 +796,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     std::vector<WfJob> wf_jobs;
     std::vector<MbChunk> mb_chunks;
     std::vector<KwJob> kw_jobs;
-    std::vector<GainJob> gain_jobs;
+    std::vector<GainJob> gain_jobs, lim_jobs;
     std::vector<int64_t> mb_delta(n_tracks, 0);
     std::vector<AttEntry> tables;
     std::map<std::tuple<double, double, double, double>, int> table_index;
@@ -801,6 +805,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     for (Wave &wv : p->waves) {
         wv.eq_lo = (int)eq_jobs.size(); wv.split_lo = (int)split_jobs.size(); wv.chain_lo = (int)chain_jobs.size();
         wv.chunk_lo = (int)mb_chunks.size(); wv.kw_lo = (int)kw_jobs.size(); wv.gain_lo = (int)gain_jobs.size();
+        wv.lim_lo = (int)lim_jobs.size();
         wv.seg_lo = n_seg_total;
         int64_t n_groups = 0;                          // group records of this wave (slot-local indices)
         for (int t = wv.track_lo; t < wv.track_hi; ++t) {
@@ -874,6 +879,18 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             for (int64_t b = 0; b < tp.n_frames; b += kGainTile)
                 gain_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
                                             tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + kGainTile, tp.n_frames), t, 0});
+            if (tp.flags & AME_F_LIMITER) {
+                // limiter tiles: a power of two >= G = look-ahead + release + 8 (a tile without an over-limit frame then
+                // guarantees the initial state at its end), as short as that allows: more tiles = more warps in flight
+                const int64_t G = (int64_t)tp.lim_frames + tp.lim_release_frames + 8;
+                int shift = 13;
+                while ((1LL << shift) < G) ++shift;
+                p->tdev[t].lim_shift = shift;
+                p->tdev[t].lim_tile0 = (int)lim_jobs.size() - wv.lim_lo;
+                for (int64_t b = 0; b < tp.n_frames; b += 1LL << shift)
+                    lim_jobs.push_back(GainJob{tp.offset_frames + tp.halo_frames + b,
+                                               tp.offset_frames + tp.halo_frames + std::min<int64_t>(b + (1LL << shift), tp.n_frames), t, 0});
+            }
         }
         {
             bool have_x = false, have_k = false;
@@ -910,8 +927,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
         wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
         wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
+        wv.lim_n = (int)lim_jobs.size() - wv.lim_lo;
         for (int t = wv.track_lo; t < wv.track_hi; ++t) wv.limiter = wv.limiter || (p->tracks[t].flags & AME_F_LIMITER);
-        p->slot_gain_jobs = std::max(p->slot_gain_jobs, wv.gain_n);
+        p->slot_lim_jobs = std::max(p->slot_lim_jobs, wv.lim_n);
         p->slot_tiles = std::max(p->slot_tiles, wv.wf_n);
         p->slot_chains = std::max(p->slot_chains, wv.chain_n);
     }
@@ -920,7 +938,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     if ((rc = upload(&p->d_tracks, p->tracks)) || (rc = upload(&p->d_tdev, p->tdev)) || (rc = upload(&p->d_mb_delta, mb_delta)) ||
         (rc = upload(&p->d_eq_jobs, eq_jobs)) || (rc = upload(&p->d_split_jobs, split_jobs)) ||
         (rc = upload(&p->d_chain_jobs, chain_jobs)) || (rc = upload(&p->d_wf_jobs, wf_jobs)) || (rc = upload(&p->d_mb_chunks, mb_chunks)) ||
-        (rc = upload(&p->d_kw_jobs, kw_jobs)) || (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_tables, tables)))
+        (rc = upload(&p->d_kw_jobs, kw_jobs)) || (rc = upload(&p->d_gain_jobs, gain_jobs)) || (rc = upload(&p->d_lim_jobs, lim_jobs)) || (rc = upload(&p->d_tables, tables)))
         return bail(rc);
     const size_t fb = (size_t)p->total_frames * 4;
     p->slots.resize(n_slots);
@@ -936,14 +954,14 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             return bail(rc);
         if (p->any_limiter &&
             ((rc = dmalloc(p, (void **)&sl.norm, (size_t)p->slot_frames * 4)) ||
-             (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(long long))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_in.st, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_out.st, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(LimState))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_in.qframe, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(int))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_out.qframe, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(int))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_in.qdelta, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(double))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_out.qdelta, (size_t)std::max(p->slot_gain_jobs, 1) * p->lim_keep * sizeof(double))) ||
-             (rc = dmalloc(p, (void **)&sl.lim_need, (size_t)std::max(p->slot_gain_jobs, 1) * sizeof(int)))))
+             (rc = dmalloc(p, (void **)&sl.lim_last, (size_t)std::max(p->slot_lim_jobs, 1) * sizeof(long long))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.st, (size_t)std::max(p->slot_lim_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.st, (size_t)std::max(p->slot_lim_jobs, 1) * sizeof(LimState))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.qframe, (size_t)std::max(p->slot_lim_jobs, 1) * p->lim_keep * sizeof(int))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.qframe, (size_t)std::max(p->slot_lim_jobs, 1) * p->lim_keep * sizeof(int))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_in.qdelta, (size_t)std::max(p->slot_lim_jobs, 1) * p->lim_keep * sizeof(double))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_out.qdelta, (size_t)std::max(p->slot_lim_jobs, 1) * p->lim_keep * sizeof(double))) ||
+             (rc = dmalloc(p, (void **)&sl.lim_need, (size_t)std::max(p->slot_lim_jobs, 1) * sizeof(int)))))
             return bail(rc);
         sl.lim_in.keep = sl.lim_out.keep = p->lim_keep;
         // the filters read a few frames past a track's end (whole 16 / 32-byte groups, never stored): keep them defined

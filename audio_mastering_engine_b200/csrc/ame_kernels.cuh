@@ -52,8 +52,10 @@ struct TrackDev {          // device-side per-track bookkeeping
     int32_t n_sb;          // number of complete 100 ms sub-blocks (halo included)
     int32_t s100;          // frames per 100 ms = (fs + 5) / 10   (ebur128.c)
     int32_t first_block;   // time shards: 400 ms blocks before this one belong to the previous shard / the warm-up
-    int32_t pad;
+    int32_t lim_tile0;     // limiter: index (within the wave's launch) of the track's first limiter tile
     int64_t n_total;       // halo + span frames
+    int32_t lim_shift;     // limiter: log2 of the track's limiter tile length (a power of two >= G)
+    int32_t pad;
 };
 
 __constant__ double c_hist_bounds[1001];
@@ -1147,21 +1149,23 @@ k_finalize(const ame_track_params *__restrict__ tracks, int track_lo, int track_
 
 // k_apply_gain: loudnorm linear mode: s16 -> x/32768 -> * gain -> lrint(x * 32768) clipped to s16.
 // Tracks with the limiter stage write the normalised signal to the slot's `norm` buffer instead of `out` (k_limiter
-// reads it) and record per tile the last frame whose peak exceeds the limiter's limit.
+// reads it) and record, per limiter tile, the last frame whose peak exceeds the limiter's limit (lim_last, preset to -1).
 __global__ void __launch_bounds__(256)
 k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restrict__ res, const ame_track_params *__restrict__ tracks,
-             const int16_t *__restrict__ pre, int16_t *__restrict__ out, int16_t *__restrict__ norm, long long *__restrict__ lim_last) {
-    __shared__ long long s_last;
+             const TrackDev *__restrict__ tdev, const int16_t *__restrict__ pre, int16_t *__restrict__ out,
+             int16_t *__restrict__ norm, long long *__restrict__ lim_last) {
     const GainJob job = jobs[blockIdx.x];
     const ame_track_result r = res[job.track];
-    const bool lim = (tracks[job.track].flags & AME_F_LIMITER) != 0;
-    const int thr_i = tracks[job.track].lim_thr_i;
+    const ame_track_params *tp = tracks + job.track;
+    const bool lim = (tp->flags & AME_F_LIMITER) != 0;
+    const int thr_i = tp->lim_thr_i;
+    const int64_t t_begin = tp->offset_frames + tp->halo_frames;
+    const int lim_tile0 = tdev[job.track].lim_tile0, lim_shift = tdev[job.track].lim_shift;
     const uint4 *src = reinterpret_cast<const uint4 *>(pre);
     uint4 *dst = reinterpret_cast<uint4 *>(lim ? norm : out);
     const int64_t v0 = job.begin >> 2, v1 = (job.end + 3) >> 2;   // 4 frames per uint4; tiles are 4-aligned
-    if (lim && threadIdx.x == 0) s_last = -1;
-    if (lim) __syncthreads();
-    long long last = -1;
+    long long last = -1;                                           // last over-limit frame seen in limiter tile `last_tile`
+    int last_tile = -1;
     const double g = r.gain;
     for (int64_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
         const uint4 q = __ldg(src + v);
@@ -1180,16 +1184,19 @@ k_apply_gain(const GainJob *__restrict__ jobs, const ame_track_result *__restric
             for (int k = 0; k < 4; ++k) {
                 const int l = (int16_t)(w[k] & 0xffffu), rr = (int16_t)(w[k] >> 16);
                 const int64_t f = 4 * v + k;
-                if (max(abs(l), abs(rr)) >= thr_i && f >= job.begin && f < job.end) last = f;
+                if (max(abs(l), abs(rr)) >= thr_i && f >= job.begin && f < job.end) {
+                    const int tile = lim_tile0 + (int)((f - t_begin) >> lim_shift);
+                    if (tile != last_tile) {
+                        if (last_tile >= 0) atomicMax(lim_last + last_tile, last);
+                        last_tile = tile;
+                    }
+                    last = f;                                      // a thread's frames only grow
+                }
             }
         }
         dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (lim) {
-        if (last >= 0) atomicMax(&s_last, last);
-        __syncthreads();
-        if (threadIdx.x == 0) lim_last[blockIdx.x] = s_last;
-    }
+    if (lim && last_tile >= 0) atomicMax(lim_last + last_tile, last);
 }
 
 // ------------------------------------------------------------------------------------------------

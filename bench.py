@@ -327,7 +327,7 @@ def run_b200(args, rank, world, local_rank):
         plan.limiter_stats()
         plan.master_device(d_in, d_out, stream=stream, fetch_results=False)
         chain_stats["limiter_open_tiles_after_round_0_1_2"] = plan.limiter_stats()
-        chain_stats["limiter_tiles"] = n_tr * (-(-n // 32768))
+        chain_stats["limiter_tiles"] = n_tr * (-(-n // 8192))
     workspace_gb = round(plan.workspace_bytes / 1e9, 2)
     plan_slots, plan_waves, stride = plan.n_slots, plan.n_waves, plan.total_frames // n_tr
     plan.close()
