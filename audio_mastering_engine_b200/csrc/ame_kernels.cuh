@@ -539,16 +539,28 @@ k_window_flag(const WfJob *__restrict__ jobs, const int16_t *__restrict__ bands,
     const bool never = job.thr_i > 32768u;         // rms <= 32768 can never exceed it
     uint32_t o[4] = {0, 0, 0, 0};
     int n_flag = 0;
+    if (t0 >= look && i0 + 8 <= n) {          // the window is full (all but the first look_frames of a chunk): one constant bound
+        const unsigned long long bound = thr2 * (unsigned long long)(2 * look);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int64_t i = i0 + k;
-        const long long s = base + pre[k];
-        const int64_t nfr = i < look ? i : look;
-        unsigned r = 0;
-        if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
-            r = isqrt_ratio((unsigned long long)s, (unsigned)(2 * nfr));
-        n_flag += r != 0;              // thr_i >= 1, so a flagged frame has rms >= 1
-        o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
+        for (int k = 0; k < 8; ++k) {
+            const unsigned long long s = (unsigned long long)(base + pre[k]);
+            unsigned r = 0;
+            if (!never && s >= bound) r = isqrt_ratio(s, (unsigned)(2 * look));
+            n_flag += r != 0;          // thr_i >= 1, so a flagged frame has rms >= 1
+            o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = i0 + k;
+            const long long s = base + pre[k];
+            const int64_t nfr = i < look ? i : look;
+            unsigned r = 0;
+            if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
+                r = isqrt_ratio((unsigned long long)s, (unsigned)(2 * nfr));
+            n_flag += r != 0;
+            o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
+        }
     }
     // flagged frames of the tile: k_compact turns the counts into each tile's rank in its chain
 #pragma unroll
