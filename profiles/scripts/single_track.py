@@ -3,11 +3,15 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from audio_mastering_engine_b200 import MasterPlan, synth
-cases = {"c1": (44100, 30.0, synth.c1_settings(), None), "c2": (48000, 180.0, synth.c2_settings(), 2.0)}
+cases = {"c1": (44100, 30.0, synth.c1_settings(), None), "c2": (48000, 180.0, synth.c2_settings(), 2.0),
+         "c2lim": (48000, 180.0, dict(synth.c2_settings(), limiter=True, true_peak=True), 2.0),
+         "c2hot": (48000, 180.0, dict(synth.c2_settings(), lufs=-6.0, limiter=True, true_peak=True), 2.0),   # clips: the limiter's worst case
+         "c5": (192000, 600.0, dict(synth.ALL_BOOST_EQ, analog_character=25, width=1.2, lufs=-14.0, multiband=True,
+                                    low_thresh=-40.0, low_ratio=10.0, mid_thresh=-40.0, mid_ratio=10.0, high_thresh=-40.0, high_ratio=10.0), "stress")}
 cw = int(os.environ.get("AME_CHAIN_WARPS", "0"))
 for name in sys.argv[1:] or ["c1", "c2"]:
     fs, secs, s, am = cases[name]
-    x = synth.track(secs, fs, 0, am_hz=am)
+    x = synth.stress_track(secs, fs, 0) if am == "stress" else synth.track(secs, fs, 0, am_hz=am)
     plan = MasterPlan([len(x)], fs, s, host_io=True, chain_warps=cw)
     h_in = torch.from_numpy(plan.pack([x])).pin_memory(); h_out = torch.empty_like(h_in).pin_memory()
     d_in = h_in.cuda(); d_out = torch.empty_like(d_in)
