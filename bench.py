@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--fs", type=int, default=48000)
     ap.add_argument("--wave-tracks", type=int, default=0, help="tracks per plan wave (0 = 32, or a sixth of the rank's tracks if fewer than 192)")
-    ap.add_argument("--slots", type=int, default=6, help="workspace slots = waves in flight")
+    ap.add_argument("--slots", type=int, default=8, help="workspace slots = waves in flight")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-wave-tracks", type=int, default=8)
     ap.add_argument("--e2e-slots", type=int, default=4)
