@@ -82,6 +82,7 @@ SYMBOLS = {
     "ame_plan_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "ame_kernel_name": (C.c_char_p, [C.c_int]),
     "ame_plan_wave_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "ame_plan_kernel_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "ame_master_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult), C.c_void_p]),
     "ame_master_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     "ame_measure_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -93,6 +94,7 @@ SYMBOLS = {
     "ame_stage_compress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_stage_loudness_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_stage_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrackResult), C.c_void_p]),
+    "ame_stage_limiter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ame_plan_tap_pre": (C.c_void_p, [C.c_void_p]),
     "ame_plan_tap_bands": (C.c_void_p, [C.c_void_p]),
     "ame_plan_tap_subblock_energy": (C.c_void_p, [C.c_void_p]),

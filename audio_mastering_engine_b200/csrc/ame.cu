@@ -278,14 +278,17 @@ int64_t pick_tile(const std::vector<int64_t> &chunks, int64_t slots, int64_t min
 // frame differs a lot between tracks (no EQ at all ... 4 stages + warmth).  Give every track the tile length
 // that makes (T + warm) * cost equal to one common budget, the smallest budget whose job count fits `slots`.
 double eq_cost_per_frame(const ame_track_params &t) {
+    // relative cost of one frame in each k_eq variant, fitted to launches of 96 identical tracks per variant
+    // (profiles/r02/eq_variant_cost.txt, warm-up overlap taken out): 4 stages = 128, 2 shelves + 1 peak = 91, one peak 57,
+    // two shelves 58, no EQ 47 (bound by its loads, not by arithmetic); warmth + 26 (+ 20 without EQ); width is free
     double c = 24.0;                                    // unpack, convert, pack, store
-    if (t.flags & AME_F_WARMTH) c += 60.0;              // two table look-ups + the 2x2 mix in explicit FP64 ops
-    if (t.flags & AME_F_WIDTH) c += 8.0;
     if (t.eq[0].kind != AME_EQ_BYPASS) c += 16.0;       // one section + blend, two channels
     if (t.eq[1].kind != AME_EQ_BYPASS) c += 36.0;       // four sections + blend, two channels
     if (t.eq[2].kind != AME_EQ_BYPASS) c += 36.0;
     if (t.eq[3].kind != AME_EQ_BYPASS) c += 16.0;
-    return c;
+    const bool warm = (t.flags & AME_F_WARMTH) != 0;
+    if (c == 24.0) return warm ? 67.0 : 47.0;
+    return c + (warm ? 26.0 : 0.0);                     // two table look-ups + the 2x2 mix in explicit FP64 ops
 }
 
 // k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
@@ -529,9 +532,42 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     return AME_OK;
 }
 
-int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, const Bufs &b, cudaStream_t s) {
+// static gain (+ the limiter's input and per-tile "last frame over the limit") and the limiter; needs d_results
+int run_apply(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_out, const Bufs &b, cudaStream_t s) {
     int16_t *d_norm = b.norm;
     long long *lim_last = b.lim_last;
+    if (!w.gain_n) return AME_OK;
+    t_begin(p, S_GAIN, s);
+    if (w.limiter) CU(cudaMemsetAsync(lim_last, 0xff, (size_t)w.lim_n * sizeof(long long), s));      // -1: no frame over the limit
+    k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, p->d_tracks, p->d_tdev, d_pre, d_out, d_norm, lim_last);
+    LAUNCH_CHECK(p);
+    t_end(p, S_GAIN, s);
+    if (w.limiter) {
+        t_begin(p, S_LIM, s);
+        const GainJob *gj = p->d_lim_jobs + w.lim_lo;
+        constexpr int kLimRounds = 2;                 // repair rounds before the sequential fallback
+        int cap = 64;
+        while (cap < p->lim_keep + 2) cap *= 2;       // queue capacity in shared memory: a power of two
+        const size_t smem = lim_smem_bytes(cap);
+        for (int round = 0; round <= kLimRounds; ++round) {
+            if (round == 0) {                         // the elementwise tiles, 256 threads each
+                k_limiter<<<w.lim_n, 256, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, 0, cap);
+                LAUNCH_CHECK(p);
+            }
+            k_limiter<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round, cap);
+            LAUNCH_CHECK(p);
+            k_lim_verify<<<(w.lim_n + 3) / 4, 128, 0, s>>>(gj, w.lim_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
+                                                             p->d_lim_stats + round);
+            LAUNCH_CHECK(p);
+        }
+        k_lim_fallback<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, cap);
+        LAUNCH_CHECK(p);
+        t_end(p, S_LIM, s);
+    }
+    return AME_OK;
+}
+
+int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_hist, int16_t *d_out, const Bufs &b, cudaStream_t s) {
     const int nt = w.track_hi - w.track_lo;
     if (nt <= 0) return AME_OK;
     t_begin(p, S_FIN, s);
@@ -539,36 +575,7 @@ int run_gain(ame_plan *p, const Wave &w, const int16_t *d_pre, const int64_t *d_
                                              p->d_tp, p->d_results);
     LAUNCH_CHECK(p);
     t_end(p, S_FIN, s);
-    if (w.gain_n) {
-        t_begin(p, S_GAIN, s);
-        if (w.limiter) CU(cudaMemsetAsync(lim_last, 0xff, (size_t)w.lim_n * sizeof(long long), s));      // -1: no frame over the limit
-        k_apply_gain<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_results, p->d_tracks, p->d_tdev, d_pre, d_out, d_norm, lim_last);
-        LAUNCH_CHECK(p);
-        t_end(p, S_GAIN, s);
-        if (w.limiter) {
-            t_begin(p, S_LIM, s);
-            const GainJob *gj = p->d_lim_jobs + w.lim_lo;
-            constexpr int kLimRounds = 2;                 // repair rounds before the sequential fallback
-            int cap = 64;
-            while (cap < p->lim_keep + 2) cap *= 2;       // queue capacity in shared memory: a power of two
-            const size_t smem = lim_smem_bytes(cap);
-            for (int round = 0; round <= kLimRounds; ++round) {
-                if (round == 0) {                         // the elementwise tiles, 256 threads each
-                    k_limiter<<<w.lim_n, 256, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, 0, cap);
-                    LAUNCH_CHECK(p);
-                }
-                k_limiter<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, lim_last, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, round, cap);
-                LAUNCH_CHECK(p);
-                k_lim_verify<<<(w.lim_n + 3) / 4, 128, 0, s>>>(gj, w.lim_n, p->d_tracks, b.lim_in, b.lim_out, b.lim_need,
-                                                                 p->d_lim_stats + round);
-                LAUNCH_CHECK(p);
-            }
-            k_lim_fallback<<<w.lim_n, 32, smem, s>>>(gj, w.lim_n, p->d_tracks, d_norm, d_out, b.lim_in, b.lim_out, b.lim_need, cap);
-            LAUNCH_CHECK(p);
-            t_end(p, S_LIM, s);
-        }
-    }
-    return AME_OK;
+    return run_apply(p, w, d_pre, d_out, b, s);
 }
 
 int run_measure(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
@@ -1131,6 +1138,29 @@ int ame_plan_kernel_times(ame_plan *p, double *ms_sum, int64_t *launches, int *n
     return AME_OK;
 }
 
+int ame_plan_kernel_timeline(ame_plan *p, int step, float *ms, int max_waves) {
+    if (!p || !ms) return fail(AME_E_INVALID, "NULL argument");
+    GUARD(p->device);
+    CU(cudaDeviceSynchronize());
+    if (p->t_used.empty() || step < 0 || step > p->t_step || step >= kMaxTimedSteps) return fail(AME_E_INVALID, "step %d was not timed", step);
+    const size_t base = (size_t)step * kMaxTimedWaves * AME_N_KERNELS;
+    const int n = std::min(std::min((int)p->waves.size(), kMaxTimedWaves), max_waves);
+    cudaEvent_t t0 = nullptr;                              // the first kernel of wave 0 opens the step
+    for (int k = 0; k < AME_N_KERNELS && !t0; ++k)
+        if (p->t_used[base + k]) t0 = p->t_ev[(base + k) * 2];
+    if (!t0) return fail(AME_E_INVALID, "step %d was not timed", step);
+    for (int w = 0; w < n; ++w)
+        for (int k = 0; k < AME_N_KERNELS; ++k) {
+            const size_t i = base + (size_t)w * AME_N_KERNELS + k;
+            float *o = ms + ((size_t)w * AME_N_KERNELS + k) * 2;
+            o[0] = o[1] = NAN;
+            if (!p->t_used[i]) continue;
+            CU(cudaEventElapsedTime(&o[0], t0, p->t_ev[i * 2]));
+            CU(cudaEventElapsedTime(&o[1], t0, p->t_ev[i * 2 + 1]));
+        }
+    return n;
+}
+
 int ame_plan_wave_timeline(ame_plan *p, float *ms, int max_waves) {
     if (!p || !ms) return fail(AME_E_INVALID, "NULL argument");
     GUARD(p->device);
@@ -1194,6 +1224,20 @@ int ame_stage_apply_gain(ame_plan *p, const int16_t *d_pre, const int64_t *d_his
         CU(cudaStreamSynchronize(s));
     }
     return AME_OK;
+}
+
+// ffmpeg alimiter alone (:223) on an int16 signal that is already normalised: the results are cleared, so that
+// k_apply_gain passes the samples through unchanged on its way to the limiter's input buffer
+int ame_stage_limiter(ame_plan *p, const int16_t *d_norm, int16_t *d_out, void *stream) {
+    if (!p || !d_norm || !d_out) return fail(AME_E_INVALID, "NULL argument");
+    SINGLE_WAVE(p);
+    GUARD(p->device);
+    for (int t = 0; t < p->n_tracks; ++t)
+        if (!(p->tracks[t].flags & AME_F_LIMITER)) return fail(AME_E_INVALID, "track %d has no limiter stage (AME_F_LIMITER)", t);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(p->d_results, 0, (size_t)p->n_tracks * sizeof(ame_track_result), s));
+    const Bufs sb = slot_bufs(p, p->waves[0], nullptr, d_out);
+    return run_apply(p, p->waves[0], d_norm, d_out, sb, s);
 }
 
 // two-phase form: every wave must keep its pre-normalisation signal between the two calls (n_slots == n_waves)

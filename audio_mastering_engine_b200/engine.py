@@ -204,6 +204,17 @@ class MasterPlan:
             L.check(n)
         return [tuple(buf[4 * w + k] for k in range(4)) for w in range(n)]
 
+    def kernel_timeline(self, step=0):
+        """[{kernel name: (begin ms, end ms)} per wave] of timed step `step` (see ame_plan_kernel_timeline)."""
+        nk, nw = L.AME_N_KERNELS, 128
+        buf = (C.c_float * (2 * nk * nw))()
+        n = self.lib.ame_plan_kernel_timeline(self.handle, int(step), buf, nw)
+        if n < 0:
+            L.check(n)
+        names = [self.lib.ame_kernel_name(i).decode() for i in range(nk)]
+        return [{names[k]: (buf[(w * nk + k) * 2], buf[(w * nk + k) * 2 + 1]) for k in range(nk)
+                 if buf[(w * nk + k) * 2] == buf[(w * nk + k) * 2]} for w in range(n)]      # NaN = not launched
+
     # stage entry points (parity taps)
     def stage_eq(self, d_in, d_pre, stream=None):
         L.check(self.lib.ame_stage_eq(self.handle, self._ptr(d_in), self._ptr(d_pre), C.c_void_p(stream or 0)))
@@ -221,6 +232,10 @@ class MasterPlan:
         L.check(self.lib.ame_stage_apply_gain(self.handle, self._ptr(d_pre), self._ptr(d_hist), self._ptr(d_out),
                                               self._results, C.c_void_p(stream or 0)))
         return self.results()
+
+    def stage_limiter(self, d_norm, d_out, stream=None):
+        """ffmpeg alimiter alone over an already normalised int16 signal (every track needs settings["limiter"])."""
+        L.check(self.lib.ame_stage_limiter(self.handle, self._ptr(d_norm), self._ptr(d_out), C.c_void_p(stream or 0)))
 
     @property
     def mb_frames(self):
@@ -283,6 +298,33 @@ def master(samples, fs, settings, device=0, chunk_seconds=30, **plan_opts):
     finally:
         plan.close()
     return (outs[0], infos[0]) if single else (outs, infos)
+
+
+LIMITER_KEYS = ("limiter", "limiter_limit", "limiter_attack", "limiter_release")
+
+
+def limit_device(d_norm, fs, settings=None, device=None):
+    """The reference's last stage alone (ffmpeg alimiter, audio_mastering_engine.py:223) on ONE track that is already
+    normalised: int16[N,2] CUDA tensor -> new int16[N,2] CUDA tensor.  A time-sharded track ends with this call on the
+    rank that gathers its spans (sharding.master_time_sharded): the limiter is one sequential state machine over the
+    whole track, so its shards cannot carry it."""
+    import torch
+    st = {k: v for k, v in (settings or {}).items() if k in LIMITER_KEYS}
+    st["limiter"] = True
+    device = d_norm.device.index if device is None else device
+    n = int(d_norm.shape[0])
+    plan = MasterPlan([n], fs, st, device=device, chunk_seconds=None)
+    try:
+        src = d_norm
+        if plan.total_frames != n:                        # the packed buffer is padded to whole groups of 8 frames
+            src = torch.zeros((plan.total_frames, 2), dtype=torch.int16, device=d_norm.device)
+            src[:n] = d_norm
+        out = torch.empty_like(src)
+        plan.stage_limiter(src, out)
+        torch.cuda.synchronize(d_norm.device)
+    finally:
+        plan.close()
+    return out[:n]
 
 
 def release_cached_memory(device=0):

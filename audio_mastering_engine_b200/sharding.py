@@ -173,19 +173,64 @@ def time_sharded_step(sh, spans, group=None):
     return out, info, moved + 2 * hist.numel() * 8
 
 
-def master_time_sharded(track, fs, settings, group=None, device=None, chunk_seconds=30, **plan_opts):
-    """Master ONE long track across the ranks of `group` (torch.distributed; NCCL on GPUs, gloo moves the two small
-    messages through the host).  Every rank passes the same track (numpy or tensor; at least its own span must be
-    valid); returns this rank's (span_begin, int16[n,2] numpy, info)."""
+def _shard_settings(settings):
+    """What the shards run: everything but the limiter, which is one sequential machine over the whole track."""
+    st = dict(settings)
+    st["limiter"] = False
+    return st
+
+
+def _gather_spans(out, spans, group, dst=0):
+    """All spans of the normalised track on rank `dst`, in order: int16[N,2] device tensor there, None elsewhere.
+    (send / recv of each non-empty span; one stereo frame travels as one int32.)"""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if rank != dst:
+        if out.shape[0]:
+            msg = out.contiguous().view(torch.int32)
+            dist.send(msg if nccl else msg.cpu(), dst=glob(dst), group=group)
+        return None
+    total = spans[-1][1]
+    full = torch.empty((total, 2), dtype=torch.int16, device=out.device)
+    for r, (lo, hi) in enumerate(spans):
+        if hi <= lo:
+            continue
+        if r == dst:
+            full[lo:hi] = out
+        else:
+            buf = torch.empty((hi - lo, 1), dtype=torch.int32, device=out.device if nccl else "cpu")
+            dist.recv(buf, src=glob(r), group=group)
+            full[lo:hi] = buf.to(out.device).view(torch.int16)
+    return full
+
+
+def master_time_sharded(track, fs, settings, group=None, device=None, chunk_seconds=30, **plan_opts):
+    """Master ONE long track across the ranks of `group` (torch.distributed; NCCL on GPUs, gloo moves the small
+    messages through the host).  Every rank passes the same track (numpy or tensor; at least its own span must be
+    valid); returns this rank's (span_begin, int16[n,2] numpy, info).
+
+    With settings["limiter"] (the reference's alimiter, :223) the normalised spans are gathered on rank 0, which runs
+    the limiter over the whole track (engine.limit_device - parallel in time on ONE GPU, but not across shards) and
+    returns (0, the whole limited track, info); the other ranks return (span_begin, an empty array, info)."""
+    import torch
+    import torch.distributed as dist
+    from .engine import limit_device
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     device = torch.cuda.current_device() if device is None else device
     spans = plan_time_shards(len(track), fs, world, chunk_seconds)
-    sh = TimeShard(spans[rank], fs, settings, rank, world, device, chunk_seconds, **plan_opts)
+    sh = TimeShard(spans[rank], fs, _shard_settings(settings), rank, world, device, chunk_seconds, **plan_opts)
     span = track[spans[rank][0]:spans[rank][1]]
     sh.load(span if hasattr(span, "device") else np.ascontiguousarray(span))
     out, info, _ = time_sharded_step(sh, spans, group)
+    if settings.get("limiter"):
+        full = _gather_spans(out, spans, group)
+        sh.close()
+        if full is None:
+            return spans[rank][0], np.zeros((0, 2), dtype=np.int16), info
+        return 0, limit_device(full, fs, settings, device).cpu().numpy(), info
     res = out.cpu().numpy()
     sh.close()
     return spans[rank][0], res, info
@@ -193,9 +238,13 @@ def master_time_sharded(track, fs, settings, group=None, device=None, chunk_seco
 
 def master_time_sharded_local(track, fs, settings, world, device=0, chunk_seconds=30, **plan_opts):
     """The same algorithm with all `world` shards emulated one after another on ONE GPU (tests, debugging):
-    halo hand-off by copy, histogram 'all-reduce' by summation.  Returns (int16[N,2], info)."""
+    halo hand-off by copy, histogram 'all-reduce' by summation, limiter (if set) over the joined spans.
+    Returns (int16[N,2], info)."""
+    import torch
+    from .engine import limit_device
     spans = plan_time_shards(len(track), fs, world, chunk_seconds)
-    shards = [TimeShard(spans[r], fs, settings, r, world, device, chunk_seconds, **plan_opts) for r in range(world)]
+    shards = [TimeShard(spans[r], fs, _shard_settings(settings), r, world, device, chunk_seconds, **plan_opts)
+              for r in range(world)]
     prev_tail = None
     hists = []
     for r, sh in enumerate(shards):
@@ -212,7 +261,10 @@ def master_time_sharded_local(track, fs, settings, world, device=0, chunk_second
     outs, info = [], None
     for sh in shards:
         o, i = sh.normalise(total)
-        outs.append(o.cpu().numpy())
+        outs.append(o.clone())
         info = info or i
         sh.close()
-    return np.concatenate(outs, axis=0), info
+    full = torch.cat(outs, dim=0)
+    if settings.get("limiter"):
+        full = limit_device(full, fs, settings, device)
+    return full.cpu().numpy(), info

@@ -192,6 +192,12 @@ const char *ame_kernel_name(int slot);
  * first copy was queued at which {its H2D copy finished, its kernels could start, its kernels finished, its D2H copy
  * finished}.  ms holds 4 * max_waves floats; returns the number of waves written, or a negative error. */
 int ame_plan_wave_timeline(ame_plan *plan, float *ms, int max_waves);
+/* where each launch of timed step `step` (0 = the first call after ame_plan_set_timing) sat on the device: ms holds
+ * 2 * AME_N_KERNELS * max_waves floats, {begin, end} per (wave, kernel slot) in milliseconds after the step's first
+ * event (slightly negative for a wave whose stream started before wave 0's), NaN for kernels the wave did not
+ * launch.  "begin" is when the wave's stream reached the launch, so a launch that waited for free SMs shows the wait
+ * as duration.  Returns the number of waves written, or a negative error. */
+int ame_plan_kernel_timeline(ame_plan *plan, int step, float *ms, int max_waves);
 
 /* the whole path: replaces the chunk loop + concat + loudnorm of
  * process_audio_with_ffmpeg_pipeline (:185-220).  d_in / d_out are DEVICE pointers to packed
@@ -234,6 +240,10 @@ int ame_stage_loudness_hist(ame_plan *plan, const int16_t *d_pre, int64_t *d_his
 /* static gain + s16 rounding (loudnorm linear mode) */
 int ame_stage_apply_gain(ame_plan *plan, const int16_t *d_pre, const int64_t *d_hist,
                          int16_t *d_out, ame_track_result *results, void *stream);
+/* ffmpeg alimiter alone (audio_mastering_engine.py:223) over a signal that is already normalised - every track of the
+ * plan must carry AME_F_LIMITER.  This is how a time-sharded track (whose shards cannot carry the limiter's sequential
+ * state) is limited after its spans have been gathered.  Clears the plan's per-track results. */
+int ame_stage_limiter(ame_plan *plan, const int16_t *d_norm, int16_t *d_out, void *stream);
 
 /* workspace taps for tests: device pointers owned by the plan (valid until destroy) */
 const int16_t *ame_plan_tap_pre(const ame_plan *plan);       /* pre-normalisation int16 */

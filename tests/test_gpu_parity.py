@@ -410,6 +410,28 @@ def test_limiter_stage_is_bit_exact(torch_cuda):
         assert np.array_equal(o, want), f
 
 
+def test_limiter_alone_and_after_time_sharding(torch_cuda):
+    """ame_stage_limiter (the limiter as its own stage: what a time-sharded track ends with on the rank that gathers
+    its spans) against the oracle's restatement, and the by-time path with the limiter on against the single plan."""
+    import torch
+    from audio_mastering_engine_b200 import limit_device, master, sharding, synth
+    from oracle import limiter
+    fs = 48000
+    for k, x in enumerate([_hot(synth.track(3.0, fs, track_id=50, am_hz=2.0), 6.0), synth.track(0.7, fs, track_id=51)[:33001],
+                           _hot(synth.track(2.0, 96000, track_id=52), 12.0)]):
+        f = 96000 if k == 2 else fs
+        got = limit_device(torch.as_tensor(x).cuda(), f).cpu().numpy()
+        assert np.array_equal(got, limiter.alimiter(x, f)), k
+    got = limit_device(torch.as_tensor(x).cuda(), 96000, dict(limiter_limit=0.8, limiter_attack=3.0, limiter_release=30.0)).cpu().numpy()
+    assert np.array_equal(got, limiter.alimiter(x, 96000, 0.8, 3.0, 30.0))
+    x = synth.track(9.0, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
+    s = dict(synth.c2_settings(), lufs=-9.0, limiter=True)         # hot target: the limiter works most of the time
+    one, info1 = master(x, fs, s, chunk_seconds=1.0)
+    many, infon = sharding.master_time_sharded_local(x, fs, s, 3, chunk_seconds=1.0)
+    assert np.array_equal(one, many) and infon["input_i"] == pytest.approx(info1["input_i"], abs=1e-9)
+    assert not np.array_equal(one, master(x, fs, dict(s, limiter=False), chunk_seconds=1.0)[0])
+
+
 def test_master_with_limiter_vs_oracle(torch_cuda):
     from audio_mastering_engine_b200 import master, synth
     from oracle import chain
@@ -499,7 +521,7 @@ def test_c4_slice_one_batch(torch_cuda):
     print("C4 slice worst LSB diff", worst)
 
 
-def _dist_worker(rank, world, port, backend, fs, seconds, chunk, out_dir):
+def _dist_worker(rank, world, port, backend, fs, seconds, chunk, out_dir, extra):
     import torch
     import torch.distributed as dist
     from audio_mastering_engine_b200 import sharding, synth
@@ -511,24 +533,28 @@ def _dist_worker(rank, world, port, backend, fs, seconds, chunk, out_dir):
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
-    begin, out, info = sharding.master_time_sharded(x, fs, synth.c2_settings(), device=dev, chunk_seconds=chunk)
+    begin, out, info = sharding.master_time_sharded(x, fs, dict(synth.c2_settings(), **extra), device=dev, chunk_seconds=chunk)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out)
     np.save(os.path.join(out_dir, f"meta{rank}.npy"), np.array([begin, info["input_i"] if info else np.nan, info["n_blocks"] if info else -1]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _run_dist(tmp_path, backend, world, fs=48000, seconds=7.0, chunk=1.0):
+def _run_dist(tmp_path, backend, world, fs=48000, seconds=7.0, chunk=1.0, extra=None):
     import socket
     import torch.multiprocessing as mp
     from audio_mastering_engine_b200 import master, synth
     sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
-    mp.spawn(_dist_worker, args=(world, port, backend, fs, seconds, chunk, str(tmp_path)), nprocs=world, join=True)
+    extra = extra or {}
+    mp.spawn(_dist_worker, args=(world, port, backend, fs, seconds, chunk, str(tmp_path), extra), nprocs=world, join=True)
     x = synth.track(seconds, fs, track_id=6, am_hz=1.0, drift_db=8.0, drift_period=3.0)
-    one, info1 = master(x, fs, synth.c2_settings(), chunk_seconds=chunk)
+    one, info1 = master(x, fs, dict(synth.c2_settings(), **extra), chunk_seconds=chunk)
     parts = [np.load(tmp_path / f"out{r}.npy") for r in range(world)]
     metas = [np.load(tmp_path / f"meta{r}.npy") for r in range(world)]
-    assert [int(m[0]) for m in metas] == list(np.cumsum([0] + [len(p) for p in parts[:-1]]))
+    if extra.get("limiter"):        # the limiter runs on rank 0 over the gathered spans: rank 0 returns the whole track
+        assert int(metas[0][0]) == 0 and all(len(q) == 0 for q in parts[1:])
+    else:
+        assert [int(m[0]) for m in metas] == list(np.cumsum([0] + [len(p) for p in parts[:-1]]))
     assert np.array_equal(np.concatenate(parts, axis=0), one)
     for m in metas:
         if m[2] >= 0:
@@ -541,6 +567,7 @@ def test_shipped_time_sharded_path_two_processes_gloo(torch_cuda, tmp_path):
     spans must equal the single-plan result bit for bit.  (No kernel waits on another process's kernel.)"""
     _run_dist(tmp_path, "gloo", 2)
     _run_dist(tmp_path, "gloo", 3, fs=44100, seconds=4.0)          # an empty-span-free ragged split
+    _run_dist(tmp_path, "gloo", 2, extra=dict(lufs=-9.0, limiter=True))      # + gather and the limiter on rank 0
 
 
 def test_shipped_time_sharded_path_nccl(torch_cuda, tmp_path):
@@ -548,6 +575,7 @@ def test_shipped_time_sharded_path_nccl(torch_cuda, tmp_path):
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run_dist(tmp_path, "nccl", 2)
+    _run_dist(tmp_path, "nccl", 2, extra=dict(lufs=-9.0, limiter=True))
 
 
 def _c_abi_shard_worker(rank, world, fs, seconds, chunk, out_dir):
