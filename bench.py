@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--precision", default="exact", choices=["exact", "fp32"])
     ap.add_argument("--limiter", action="store_true", help="also run the final alimiter stage (:223; not part of north_star (a)-(d))")
     ap.add_argument("--true-peak", action="store_true", help="also measure the BS.1770 true peak")
+    ap.add_argument("--ablate", default="", help="experiments only (profiles/r02/ablation.txt): comma list of "
+                    "nomb (no track multiband), allmb, noeq (EQ preset None, no warmth, width 1), nolufs")
     return ap.parse_args()
 
 
@@ -291,6 +293,10 @@ def run_b200(args, rank, world, local_rank):
         n_tr, first = len(mine), mine.start
     ids = batch_order(list(range(first, first + n_tr)), synth, EQ_PRESETS)
     settings = [dict(synth.c4_settings(t, EQ_PRESETS), limiter=args.limiter, true_peak=args.true_peak) for t in ids]
+    for a in filter(None, args.ablate.split(",")):
+        over = {"nomb": dict(multiband=False), "allmb": dict(multiband=True), "nolufs": dict(lufs=None),
+                "noeq": dict(bass_boost=0.0, mid_cut=0.0, presence_boost=0.0, treble_boost=0.0, analog_character=0, width=1.0)}[a]
+        settings = [dict(s, **over) for s in settings]
     wave_tracks = args.wave_tracks if args.wave_tracks > 0 else (32 if n_tr >= 192 else max(1, -(-n_tr // 6)))
     n_waves = max(1, -(-n_tr // wave_tracks))
     plan_kw = dict(device=local_rank, chain_warps=args.chain_warps, kw_tile_subblocks=args.kw_tile,
@@ -485,6 +491,8 @@ def run_b200(args, rank, world, local_rank):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "parity_check": parity, "time_sharded": time_sharded, "workspace_gb": workspace_gb,
                 "workspace_over_input": round(workspace_gb / (frames_rank * 4 / 1e9), 2), "chain_stats": chain_stats}
+        if args.ablate:
+            line["config"]["ablation"] = args.ablate + " (an experiment on a changed workload, not a bench value)"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
