@@ -469,12 +469,15 @@ int run_split(ame_plan *p, const Wave &w, const int16_t *d_pre, int16_t *d_bands
 }
 
 // Lanes (time segments) per chain of k_att_chain.  More lanes = shorter segments = cheaper passes but more of them once
-// a segment is shorter than the distance after which trajectories meet; the pass cost is so low on the dense list
-// that 4 warps are right from one track to the full batch, 8 when only a few chains share the machine.
+// a segment is shorter than the distance after which trajectories meet.  Alone on the GPU a chain is fastest with 8
+// warps (few chains) or 4; in a batch, where launches of several waves share the SMs, a 216-register lane is worth
+// more as room for the other kernels than as a shorter segment: 2 warps (1024 tracks: 223-225 ms per step against
+// 228 with 4 warps and 239 with 6, profiles/r02/scheduling_experiments.txt).
 int chain_lanes(const ame_plan *p, int n_chains) {
     if (p->chain_warps < 0) return 1;                       // ONE lane per chain: the sequential loop
     if (p->chain_warps > 0) return 32 * p->chain_warps;
-    return n_chains * 2 <= p->n_sm ? 256 : 128;
+    if (n_chains * 2 <= p->n_sm) return 256;
+    return (n_chains >= p->n_sm && p->slots.size() > 1) ? 64 : 128;
 }
 
 int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
