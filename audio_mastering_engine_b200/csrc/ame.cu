@@ -483,9 +483,13 @@ int chain_lanes(const ame_plan *p, int n_chains) {
 int run_compress(ame_plan *p, const Wave &w, const Bufs &b, cudaStream_t s) {
     if (!w.chain_n) return AME_OK;
     t_begin(p, S_FLAG, s);
-    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, b.bands, b.rms, b.tile_cnt);
+    int *tile_base = b.tile_cnt + std::max(p->slot_tiles, 1);
+    k_window_flag<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, b.bands, b.rms, b.tile_cnt, b.grp);
     LAUNCH_CHECK(p);
-    k_compact<<<w.wf_n, kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, w.chain_lo, b.rms, b.tile_cnt, b.list, b.grp, b.n_flagged);
+    k_tile_prefix<<<w.chain_n, kWfThreads, 0, s>>>(p->d_chain_jobs + w.chain_lo, b.tile_cnt, tile_base, b.n_flagged);
+    LAUNCH_CHECK(p);
+    k_compact<<<(w.wf_n + kWfThreads / 32 - 1) / (kWfThreads / 32), kWfThreads, 0, s>>>(p->d_wf_jobs + w.wf_lo, w.wf_n, b.rms, b.tile_cnt,
+                                                                                          tile_base, b.list, b.grp);
     LAUNCH_CHECK(p);
     t_end(p, S_FLAG, s);
     t_begin(p, S_CHAIN, s);
@@ -957,7 +961,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             (rc = dmalloc(p, (void **)&sl.bands, (size_t)p->mb_frames * 4 * 3)) ||
             (rc = dmalloc(p, (void **)&sl.rms, (size_t)p->mb_frames * 2 * 3)) ||
             (rc = dmalloc(p, (void **)&sl.list, (size_t)p->mb_frames * 2 * 3)) ||
-            (rc = dmalloc(p, (void **)&sl.tile_cnt, (size_t)std::max(p->slot_tiles, 1) * sizeof(int))) ||
+            (rc = dmalloc(p, (void **)&sl.tile_cnt, (size_t)std::max(p->slot_tiles, 1) * 2 * sizeof(int))) ||     // counts, then ranks
             (rc = dmalloc(p, (void **)&sl.n_flagged, (size_t)std::max(p->slot_chains, 1) * sizeof(int))) ||
             (rc = dmalloc(p, (void **)&sl.grp, (size_t)p->slot_groups * sizeof(GrpRec))) ||
             (rc = dmalloc(p, (void **)&sl.att, (size_t)p->mb_frames * 8 * 3)))

@@ -485,13 +485,14 @@ __device__ __forceinline__ unsigned isqrt_ratio(unsigned long long s, unsigned n
     return r;
 }
 
+struct GrpRec { uint32_t mask, base; };   // per 32-frame group of a chain: flagged frames, flagged frames before the group
+
 __global__ void __launch_bounds__(kWfThreads)
 k_window_flag(const WfJob *__restrict__ jobs, const int16_t *__restrict__ bands, uint16_t *__restrict__ rms,
-              int *__restrict__ tile_cnt) {
+              int *__restrict__ tile_cnt, GrpRec *__restrict__ grp) {
     __shared__ long long s_scan[kWfThreads / 32];
     __shared__ unsigned long long s_head[kWfThreads / 32];
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ int s_flag[kWfThreads / 32];
     const WfJob job = jobs[blockIdx.x];
     const uint32_t *bp = reinterpret_cast<const uint32_t *>(bands) + job.plane_off;
     uint16_t *rp = rms + job.plane_off;
@@ -538,7 +539,7 @@ k_window_flag(const WfJob *__restrict__ jobs, const int16_t *__restrict__ bands,
     const unsigned long long thr2 = (unsigned long long)job.thr_i * job.thr_i;
     const bool never = job.thr_i > 32768u;         // rms <= 32768 can never exceed it
     uint32_t o[4] = {0, 0, 0, 0};
-    int n_flag = 0;
+    unsigned m8 = 0;                               // flagged frames of this thread (thr_i >= 1, so a flagged frame has rms >= 1)
     if (t0 >= look && i0 + 8 <= n) {          // the window is full (all but the first look_frames of a chunk): one constant bound
         const unsigned long long bound = thr2 * (unsigned long long)(2 * look);
 #pragma unroll
@@ -546,7 +547,7 @@ k_window_flag(const WfJob *__restrict__ jobs, const int16_t *__restrict__ bands,
             const unsigned long long s = (unsigned long long)(base + pre[k]);
             unsigned r = 0;
             if (!never && s >= bound) r = isqrt_ratio(s, (unsigned)(2 * look));
-            n_flag += r != 0;          // thr_i >= 1, so a flagged frame has rms >= 1
+            m8 |= (r != 0 ? 1u : 0u) << k;
             o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
         }
     } else {
@@ -558,23 +559,39 @@ k_window_flag(const WfJob *__restrict__ jobs, const int16_t *__restrict__ bands,
             unsigned r = 0;
             if (!never && i < n && nfr > 0 && (unsigned long long)s >= thr2 * (unsigned long long)(2 * nfr))
                 r = isqrt_ratio((unsigned long long)s, (unsigned)(2 * nfr));
-            n_flag += r != 0;
+            m8 |= (r != 0 ? 1u : 0u) << k;
             o[k >> 1] |= (r & 0xffffu) << ((k & 1) * 16);
         }
     }
-    // flagged frames of the tile: k_compact turns the counts into each tile's rank in its chain
+    // rank of every flagged frame inside the tile: exclusive scan of the per-thread counts over the CTA
+    const int cnt = __popc(m8);
+    int fincl = cnt;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n_flag += __shfl_xor_sync(kFull, n_flag, d);
-    if (lane == 0 && n_flag) atomicAdd(&s_cnt, n_flag);
-    if (i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(rp + i0) & 15) == 0)) {
-        *reinterpret_cast<uint4 *>(rp + i0) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFull, fincl, d);
+        if (lane >= d) fincl += v;
+    }
+    if (lane == 31) s_flag[wid] = fincl;
+    // the four threads of a 32-frame group sit in one warp (threadIdx.x & 3 == 0 leads)
+    const unsigned m1 = __shfl_down_sync(kFull, m8, 1), m2 = __shfl_down_sync(kFull, m8, 2), m3 = __shfl_down_sync(kFull, m8, 3);
+    __syncthreads();
+    int fbase = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < kWfThreads / 32; ++q) {
+        if (q < wid) fbase += s_flag[q];
+        total += s_flag[q];
+    }
+    const int rank = fbase + fincl - cnt;
+    if ((threadIdx.x & 3) == 0 && i0 < n)
+        grp[job.grp_begin + (i0 >> 5)] = GrpRec{m8 | (m1 << 8) | (m2 << 16) | (m3 << 24), (uint32_t)rank};   // k_compact adds the tile's rank
+    if (m8) {                  // the tile's flagged rms values, dense from the tile's first slot of the rms plane
+        uint16_t *dp = rp + t0 + rank;
+        int slot = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (i0 + k < n) rp[i0 + k] = (uint16_t)(o[k >> 1] >> ((k & 1) * 16));
+            if (m8 & (1u << k)) dp[slot++] = (uint16_t)((o[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_cnt;
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
 // att' = (att <= M) ? min(att + inc, M) : max(att - dec, 0), evaluated as
@@ -615,8 +632,6 @@ __device__ __forceinline__ double att_update(double att, double m, double inc, d
 // The walk is a software pipeline: rms values two 8-step blocks ahead, table entries (one 32-byte gather per step)
 // one block ahead, 25 cycles per dependent step (profiles/micro/att_chain_latency3.cu).
 // ------------------------------------------------------------------------------------------------
-struct GrpRec { uint32_t mask, base; };   // per 32-frame group of a chain: flagged frames, flagged frames before the group
-
 constexpr int kChainMaxThreads = 256;
 
 struct RmsBlk { uint32_t w[4]; };         // 8 consecutive entries of the dense rms list
@@ -636,61 +651,60 @@ __device__ __forceinline__ RmsBlk list_load(const uint16_t *__restrict__ lp, int
     return q;
 }
 
-// k_compact: one CTA per k_window_flag tile (2048 frames of one chain).  The tile's rank in its chain is the sum of
-// the flagged counts of the chain's earlier tiles (a few hundred ints, read from L2); inside the tile a CTA-wide
-// exclusive scan gives every flagged frame its rank.  Writes the rms values of the flagged frames to the chain's
-// dense list, the group records, and - from the chain's last tile - the chain's flagged-frame count.
+// k_tile_prefix: one CTA per chain.  tile_base[j] = flagged frames of the chain in front of its tile j (exclusive scan of
+// the k_window_flag counts, a few hundred ints); n_flagged = the chain's total.
 __global__ void __launch_bounds__(kWfThreads)
-k_compact(const WfJob *__restrict__ jobs, int chain_lo, const uint16_t *__restrict__ rms, const int *__restrict__ tile_cnt,
-          uint16_t *__restrict__ list, GrpRec *__restrict__ grp, int *__restrict__ n_flagged) {
-    __shared__ int s_warp[kWfThreads / 32], s_before[kWfThreads / 32];
-    const WfJob job = jobs[blockIdx.x];
+k_tile_prefix(const ChainJob *__restrict__ jobs, const int *__restrict__ tile_cnt, int *__restrict__ tile_base,
+              int *__restrict__ n_flagged) {
+    __shared__ int s_warp[kWfThreads / 32];
+    const ChainJob job = jobs[blockIdx.x];
+    const int n_tiles = (int)((job.n + kWfTile - 1) / kWfTile);
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int tile = (int)blockIdx.x;
-    const int mine = tile_cnt[tile];
-    const bool last = job.tile_begin + kWfTile >= job.n;
-    // flagged frames of the chain in front of this tile
-    int before = 0;
-    for (int j = job.tile0 + t; j < tile; j += kWfThreads) before += tile_cnt[j];
+    int carry = 0;
+    for (int j0 = 0; j0 < n_tiles; j0 += kWfThreads) {
+        const int j = j0 + t;
+        const int c = j < n_tiles ? tile_cnt[job.tile0 + j] : 0;
+        int incl = c;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(kFull, before, d);
-    if (lane == 0) s_before[wid] = before;
-    const uint16_t *rp = rms + job.plane_off;
-    uint16_t *lp = list + job.plane_off;
-    GrpRec *gr = grp + job.grp_begin;
-    const int64_t n = job.n, i = job.tile_begin + (int64_t)t * 8;
-    const bool vec = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
-    const RmsBlk q = list_load(rp, i, n, vec);
-    unsigned m8 = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        int base = carry, total = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if ((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu) m8 |= 1u << k;
-    const int cnt = __popc(m8);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += v;
+        for (int q = 0; q < kWfThreads / 32; ++q) {
+            if (q < wid) base += s_warp[q];
+            total += s_warp[q];
+        }
+        if (j < n_tiles) tile_base[job.tile0 + j] = base + incl - c;
+        carry += total;
+        __syncthreads();
     }
-    if (lane == 31) s_warp[wid] = incl;
-    // the four threads of a 32-frame group sit in one warp (t & 3 == 0 leads)
-    const unsigned m1 = __shfl_down_sync(kFull, m8, 1), m2 = __shfl_down_sync(kFull, m8, 2), m3 = __shfl_down_sync(kFull, m8, 3);
-    __syncthreads();
-    int base = 0;
-#pragma unroll
-    for (int w = 0; w < kWfThreads / 32; ++w) {
-        base += s_before[w];
-        if (w < wid) base += s_warp[w];
+    if (t == 0) n_flagged[blockIdx.x] = carry;
+}
+
+// k_compact: one WARP per k_window_flag tile.  Moves the tile's dense run of flagged rms values (the tile's first
+// tile_cnt slots of the rms plane) to its place in the chain's dense list and adds the tile's rank to the tile's group
+// records (64 of them).
+__global__ void __launch_bounds__(kWfThreads)
+k_compact(const WfJob *__restrict__ jobs, int n_tiles, const uint16_t *__restrict__ rms, const int *__restrict__ tile_cnt,
+          const int *__restrict__ tile_base, uint16_t *__restrict__ list, GrpRec *__restrict__ grp) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (kWfThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const WfJob job = jobs[tile];
+    const int cnt = tile_cnt[tile], base = tile_base[tile];
+    if (base) {                                            // the first tiles of a chain (rank 0) keep their records
+        const int64_t frames = min((int64_t)kWfTile, job.n - job.tile_begin);
+        const int ng = (int)((frames + 31) >> 5);
+        GrpRec *gr = grp + job.grp_begin + (job.tile_begin >> 5);
+        for (int g = lane; g < ng; g += 32) gr[g].base += (uint32_t)base;
     }
-    const int rank = base + incl - cnt;
-    if ((t & 3) == 0 && i < n) gr[i >> 5] = GrpRec{m8 | (m1 << 8) | (m2 << 16) | (m3 << 24), (uint32_t)rank};
-    if (mine) {
-        int slot = rank;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (m8 & (1u << k)) lp[slot++] = (uint16_t)((q.w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-    }
-    if (last && t == kWfThreads - 1) n_flagged[job.chain - chain_lo] = rank + cnt;
+    const uint16_t *rp = rms + job.plane_off + job.tile_begin;
+    uint16_t *lp = list + job.plane_off + base;
+    for (int j = lane; j < cnt; j += 32) lp[j] = rp[j];
 }
 
 
