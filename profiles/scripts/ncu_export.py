@@ -43,7 +43,7 @@ def main():
         if name in seen:                                               # the capture may run into the next step: one launch per kernel
             continue
         seen.add(name)
-        name = {"k_compact": "k_window_flag"}.get(name, name)          # timed (and counted) with k_window_flag
+        name = {"k_compact": "k_window_flag", "k_tile_prefix": "k_window_flag"}.get(name, name)   # timed (and counted) with k_window_flag
         rd = float(r[hdr.index("dram__bytes_read.sum")]) * scale[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(r[hdr.index("dram__bytes_write.sum")]) * scale[units[hdr.index("dram__bytes_write.sum")]]
         ms = float(r[hdr.index("gpu__time_duration.sum")]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[units[hdr.index("gpu__time_duration.sum")]]
