@@ -132,6 +132,7 @@ struct Wave {
     int64_t seg_lo = 0, seg_hi = 0;
     int slot = 0;                                  // workspace slot (and stream) this wave runs in
     bool limiter = false;                          // a track of the wave has the limiter stage
+    bool true_peak = false;                        // a track of the wave wants its oversampled peak
     int64_t mb_frames = 0, n_groups = 0;           // of the wave's own multiband packing
     bool xover_uni = false, kw_uni = false;        // all multiband tracks share the crossover / all k_kweight_energy tracks the K filter
     XoverCfg xover{};
@@ -526,7 +527,7 @@ int run_hist(ame_plan *p, const Wave &w, const int16_t *d_pre, int64_t *d_hist, 
     LAUNCH_CHECK(p);
     t_end(p, S_TAIL, s);
     CU(cudaMemsetAsync(p->d_tp + w.track_lo, 0, (size_t)nt * 4, s));
-    if (p->any_tp && w.gain_n) {
+    if (w.true_peak && w.gain_n) {
         t_begin(p, S_TP, s);
         k_true_peak<<<w.gain_n, 256, 0, s>>>(p->d_gain_jobs + w.gain_lo, p->d_tracks, d_pre, p->d_tp);
         LAUNCH_CHECK(p);
@@ -942,7 +943,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.chunk_n = (int)mb_chunks.size() - wv.chunk_lo; wv.kw_n = (int)kw_jobs.size() - wv.kw_lo;
         wv.gain_n = (int)gain_jobs.size() - wv.gain_lo; wv.seg_hi = n_seg_total;
         wv.lim_n = (int)lim_jobs.size() - wv.lim_lo;
-        for (int t = wv.track_lo; t < wv.track_hi; ++t) wv.limiter = wv.limiter || (p->tracks[t].flags & AME_F_LIMITER);
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) {
+            wv.limiter = wv.limiter || (p->tracks[t].flags & AME_F_LIMITER);
+            wv.true_peak = wv.true_peak || (p->tracks[t].flags & AME_F_TRUE_PEAK);
+        }
         p->slot_lim_jobs = std::max(p->slot_lim_jobs, wv.lim_n);
         p->slot_tiles = std::max(p->slot_tiles, wv.wf_n);
         p->slot_chains = std::max(p->slot_chains, wv.chain_n);

@@ -920,7 +920,7 @@ __device__ __noinline__ double gain_of_att(double att) { return exp10(-att / 20.
 // list value of the last flagged frame at or before it: rank = group base + popc(mask up to the lane); 0 before the
 // first flagged frame of the chunk.  gain = 10^(-att/20) (pydub db_to_float), audioop.mul = floor(clip(x * gain)),
 // skipped when att == 0 exactly as pydub does, then low.overlay(mid).overlay(high) = saturating adds (:309).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_lo, int64_t seg_hi,
                  const int16_t *__restrict__ bands, const GrpRec *__restrict__ grp, const double *__restrict__ att,
                  int16_t *__restrict__ pre, int64_t mb_frames) {
@@ -951,22 +951,26 @@ k_compress_apply(const MbChunk *__restrict__ chunks, int n_chunks, int64_t seg_l
             rec[b][g] = GrpRec{r.x, r.y};
         }
     }
-    int accl[8], accr[8];
+    // the attenuation in force at every (band, frame): all 24 gathers in flight before the first one is used
+    double av[3][8];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const double *ap = att + (int64_t)b * mb_frames + ck.mb_begin;
-        double av[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const unsigned rank = rec[b][g].base + __popc(rec[b][g].mask & (0xffffffffu >> (31 - lane)));
-            av[g] = rank ? __ldg(ap + (rank - 1)) : 0.0;
+            av[b][g] = rank ? __ldg(ap + (rank - 1)) : 0.0;
         }
+    }
+    int accl[8], accr[8];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
         double c_att = 0.0, c_fac = 1.0;           // per-lane cache of the last gain computed
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const uint32_t w = wv[b][g];
             int l = (int16_t)(w & 0xffffu), r = (int16_t)(w >> 16);
-            const double mine = av[g];
+            const double mine = av[b][g];
             if (mine != 0.0) {
                 if (mine != c_att) { c_att = mine; c_fac = gain_of_att(mine); }
                 l = mul_floor(l, c_fac);

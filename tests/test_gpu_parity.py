@@ -258,6 +258,41 @@ def test_host_path_waves_equal_single_wave(torch_cuda):
         assert [i["input_i"] for i in ia] == [i["input_i"] for i in ib]
 
 
+def test_kernel_timing_exports(torch_cuda):
+    """ame_plan_set_timing / kernel_times / kernel_timeline: every kernel the settings need shows up once per wave, begins
+    before it ends, follows its predecessor in the wave's stream, and timing does not change the bytes that come out."""
+    import torch
+    from audio_mastering_engine_b200 import MasterPlan, synth, EQ_PRESETS
+    fs = 48000
+    tracks = [synth.track(1.0, fs, track_id=k, am_hz=2.0) for k in range(6)]
+    sets = [dict(synth.c4_settings(k, EQ_PRESETS), limiter=(k == 2), true_peak=(k == 3)) for k in range(6)]
+    plan = MasterPlan([len(t) for t in tracks], fs, sets, chunk_seconds=0.5, n_waves=3, n_slots=2)
+    d_in = torch.as_tensor(plan.pack(tracks)).cuda()
+    ref, out = torch.empty_like(d_in), torch.empty_like(d_in)
+    plan.master_device(d_in, ref)
+    plan.set_timing(True)
+    for _ in range(2):
+        plan.master_device(d_in, out)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, out)
+    times, steps = plan.kernel_times()
+    assert steps == 2
+    assert times["k_eq"][1] == 2 * 3 and times["k_apply_gain"][1] == 6 and times["k_eq"][0] > 0
+    assert times["k_window_flag"][1] == 6 and times["k_att_chain"][1] == 6           # every wave has a multiband track
+    assert times["k_limiter"][1] == 2 and times["k_true_peak"][1] == 2               # one wave each
+    tl = plan.kernel_timeline(1)
+    assert len(tl) == 3
+    order = ["k_eq", "k_band_split", "k_window_flag", "k_att_chain", "k_compress_apply", "k_kweight_energy", "k_apply_gain"]
+    for w in tl:
+        assert all(b <= e for b, e in w.values())
+        ends = [w[k][1] for k in order if k in w]
+        begins = [w[k][0] for k in order if k in w]
+        assert all(begins[i + 1] >= ends[i] - 1e-3 for i in range(len(ends) - 1)), w      # stream order inside a wave
+    with pytest.raises(Exception):
+        plan.kernel_timeline(5)
+    plan.close()
+
+
 def test_random_settings_sweep(torch_cuda):
     """Randomised settings over the GUI slider ranges (mastering_gui.py:44-55) and several sample rates, one
     batch per rate, every track against the oracle."""
