@@ -783,12 +783,30 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         min_s100 = std::min(min_s100, p->tdev[t].s100);
     }
     const int64_t n_sb_kw = p->n_sb_total;
+    // One warp per scheduler already gives these FP64-bound kernels ~77 % of the throughput of two (k_eq alone: 13.7 vs
+    // 10.6 ms), and every tile pays its warm-up once: when a wave is so small that a full set of resident threads would
+    // make the tiles shorter than ~1.2 x the warm-up (one long 192 kHz track), half the threads do the job sooner -
+    // (2T + W) / (2T * 0.77) < (T + W) / T  <=>  T < 1.17 W.
+    auto fewer_threads = [](int64_t slots, double frames, double warm_weighted) {
+        const double tile = frames / (double)slots, warm = frames > 0 ? warm_weighted / frames : 0.0;
+        return (tile < 1.17 * warm && slots >= 512) ? slots / 2 : slots;
+    };
     for (const Wave &wv : p->waves) {
         std::vector<int64_t> cm;
-        for (int t = wv.track_lo; t < wv.track_hi; ++t)
-            if (p->tracks[t].flags & AME_F_MULTIBAND) cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
-        split_tile = std::max(split_tile, pick_tile(cm, split_slots, kMinTile));
-        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi, eq_slots, kMinTile);
+        double eq_frames = 0, eq_warm = 0, mb_fr = 0, mb_warm = 0;
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) {
+            const ame_track_params &tp = p->tracks[t];
+            eq_frames += (double)tp.n_frames;
+            eq_warm += (double)tp.n_frames * tp.warm_eq;
+            if (tp.flags & AME_F_MULTIBAND) {
+                cm.insert(cm.end(), chunks_all[t].begin(), chunks_all[t].end());
+                mb_fr += (double)tp.n_frames;
+                mb_warm += (double)tp.n_frames * tp.warm_xover;
+            }
+        }
+        split_tile = std::max(split_tile, pick_tile(cm, fewer_threads(split_slots, mb_fr, mb_warm), kMinTile));
+        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi,
+                                                       fewer_threads(eq_slots, eq_frames, eq_warm), kMinTile);
         for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
     }
     p->eq_tile = 0;

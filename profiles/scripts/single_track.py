@@ -8,10 +8,15 @@ cases = {"c1": (44100, 30.0, synth.c1_settings(), None), "c2": (48000, 180.0, sy
          "c2hot": (48000, 180.0, dict(synth.c2_settings(), lufs=-6.0, limiter=True, true_peak=True), 2.0),   # clips: the limiter's worst case
          "c5": (192000, 600.0, dict(synth.ALL_BOOST_EQ, analog_character=25, width=1.2, lufs=-14.0, multiband=True,
                                     low_thresh=-40.0, low_ratio=10.0, mid_thresh=-40.0, mid_ratio=10.0, high_thresh=-40.0, high_ratio=10.0), "stress")}
+cases["c3"] = (96000, 3600.0, synth.c2_settings(), "device")         # generated on the GPU (the numpy recipe takes minutes at this length)
 cw = int(os.environ.get("AME_CHAIN_WARPS", "0"))
 for name in sys.argv[1:] or ["c1", "c2"]:
     fs, secs, s, am = cases[name]
-    x = synth.stress_track(secs, fs, 0) if am == "stress" else synth.track(secs, fs, 0, am_hz=am)
+    if am == "device":
+        x = synth.torch_track_batch(1, secs, fs, torch.device("cuda", 0))[0].cpu().numpy()
+        torch.cuda.empty_cache()
+    else:
+        x = synth.stress_track(secs, fs, 0) if am == "stress" else synth.track(secs, fs, 0, am_hz=am)
     plan = MasterPlan([len(x)], fs, s, host_io=True, chain_warps=cw)
     h_in = torch.from_numpy(plan.pack([x])).pin_memory(); h_out = torch.empty_like(h_in).pin_memory()
     d_in = h_in.cuda(); d_out = torch.empty_like(d_in)
