@@ -1024,61 +1024,50 @@ k_kweight_energy(const __grid_constant__ KwCfg kc, const KwJob *__restrict__ job
     const int n_it = (int)((t_end - f_lo + 7) >> 3);             // 8 frames = one 32-byte sector per iteration
     uint4 c0 = ldg16(src), c1 = ldg16(src + 1), n0 = c0, n1 = c1;
     if (n_it > 1) { n0 = ldg16(src + 2); n1 = ldg16(src + 3); }
-    if ((s100 & 7) == 0) {
-        // 48 / 96 / 192 kHz: sub-blocks are whole 8-frame groups, so the warm-up groups only filter and the others
-        // accumulate without a per-frame test (a third of the generic loop's instructions are those tests)
-        const int n_warm = (int)((t_begin - f_lo) >> 3);
-        const int per_sb = (int)(s100 >> 3);
-        int left = per_sb;
-        for (int it = 0; it < n_it; ++it) {
-            uint4 m0 = n0, m1 = n1;
-            if (it + 2 < n_it) { m0 = ldg16(src + 2 * it + 4); m1 = ldg16(src + 2 * it + 5); }
-            const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            if (it < n_warm) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
-                    bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
-                    bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
-                    const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
-                    const double yr = bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
-                    accl = fma(yl, yl, accl);
-                    accr = fma(yr, yr, accr);
-                    pk = max(pk, max(abs(xl), abs(xr)));
-                }
-                if (--left == 0) {
-                    energy[td.sb_offset + sb] = accl + accr;         // ebur128: per-channel sums, then added
-                    accl = 0; accr = 0; ++sb; left = per_sb;
-                }
-            }
-            c0 = n0; c1 = n1; n0 = m0; n1 = m1;
-        }
-        atomicMax(peak + job.track, pk);
-        return;
-    }
+    // Three kinds of 8-frame groups: in front of the tile (warm-up: filter only), inside one sub-block of the tile
+    // (accumulate, no per-frame test - all of them at 48 / 96 / 192 kHz, where a sub-block is a whole number of groups),
+    // and the ones a tile or sub-block boundary cuts (per-frame tests; 44.1 kHz: one group in 551).
     for (int it = 0; it < n_it; ++it) {
         uint4 m0 = n0, m1 = n1;
         if (it + 2 < n_it) { m0 = ldg16(src + 2 * it + 4); m1 = ldg16(src + 2 * it + 5); }
         const int64_t g = f_lo + 8 * (int64_t)it;
         const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        if (g + 8 <= t_begin) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int64_t f = g + k;
-            const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
-            const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
-            const double yr = bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
-            if (f >= t_begin && f < t_end) {
+            for (int k = 0; k < 8; ++k) {
+                const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
+                bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
+                bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
+            }
+        } else if (g >= t_begin && g + 8 <= next_end) {          // next_end <= t_end
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
+                const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
+                const double yr = bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
                 accl = fma(yl, yl, accl);
                 accr = fma(yr, yr, accr);
                 pk = max(pk, max(abs(xl), abs(xr)));
-                if (f + 1 == next_end) {
-                    energy[td.sb_offset + sb] = accl + accr;     // ebur128: per-channel sums, then added
-                    accl = 0; accr = 0; ++sb; next_end += s100;
+            }
+            if (g + 8 == next_end) {
+                energy[td.sb_offset + sb] = accl + accr;         // ebur128: per-channel sums, then added
+                accl = 0; accr = 0; ++sb; next_end += s100;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t f = g + k;
+                const int xl = (int)(int16_t)(w[k] & 0xffffu), xr = (int)(int16_t)(w[k] >> 16);
+                const double yl = bq_step(k1, zl[2], zl[3], bq_step(k0, zl[0], zl[1], i16_to_unit(xl)));
+                const double yr = bq_step(k1, zr[2], zr[3], bq_step(k0, zr[0], zr[1], i16_to_unit(xr)));
+                if (f >= t_begin && f < t_end) {
+                    accl = fma(yl, yl, accl);
+                    accr = fma(yr, yr, accr);
+                    pk = max(pk, max(abs(xl), abs(xr)));
+                    if (f + 1 == next_end) {
+                        energy[td.sb_offset + sb] = accl + accr;
+                        accl = 0; accr = 0; ++sb; next_end += s100;
+                    }
                 }
             }
         }
