@@ -789,6 +789,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     // (2T + W) / (2T * 0.77) < (T + W) / T  <=>  T < 1.17 W.
     auto fewer_threads = [](int64_t slots, double frames, double warm_weighted) {
         const double tile = frames / (double)slots, warm = frames > 0 ? warm_weighted / frames : 0.0;
+        if (std::getenv("AME_FULL_THREADS")) return slots;      // experiments
         return (tile < 1.17 * warm && slots >= 512) ? slots / 2 : slots;
     };
     for (const Wave &wv : p->waves) {
