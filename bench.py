@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-serial-pass", action="store_true")
+    ap.add_argument("--serial-wave-tracks", type=int, default=128, help="tracks per launch of the serialised (roofline) pass: the "
+                    "launch shape of the tracked ncu capture")
     ap.add_argument("--no-time-sharded", action="store_true")
     ap.add_argument("--time-sharded-seconds", type=float, default=3600.0)
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
@@ -350,7 +352,8 @@ def run_b200(args, rank, world, local_rank):
     mb_frames = sum(1 for s in settings if s["multiband"]) * n
     roofline = None
     if not args.no_serial_pass:
-        splan = MasterPlan([n] * n_tr, fs, settings, n_waves=n_waves, n_slots=1, **plan_kw)
+        ser_waves = max(1, -(-n_tr // max(args.serial_wave_tracks, 1)))
+        splan = MasterPlan([n] * n_tr, fs, settings, n_waves=ser_waves, n_slots=1, **plan_kw)
         d_chk = torch.empty_like(d_out)
         splan.master_device(d_in, d_chk, stream=stream, fetch_results=False)
         torch.cuda.synchronize()
@@ -398,7 +401,9 @@ def run_b200(args, rank, world, local_rank):
                               "note": "whole step of the timed (overlapped) run at 16 B per stereo frame"},
                     "serialised_pass": {"ms_per_step": round(ser_ms, 3), "sum_of_kernel_ms": round(sum(r["ms_per_step"] for r in per_kernel.values()), 3),
                                         "equals_timed_output": serial_equal,
-                                        "note": "one-slot plan: every launch alone on the GPU, CUDA events on its stream"},
+                                        "waves": ser_waves,
+                                        "note": "one-slot plan in waves of up to %d tracks (the launch shape of the ncu capture): every "
+                                                "launch alone on the GPU, CUDA events on its stream" % args.serial_wave_tracks},
                     "per_kernel": per_kernel}
 
     # ---- parity: three tracks of the timed batch against the CPU oracle (outside every timed region) -------------
