@@ -292,36 +292,52 @@ double eq_cost_per_frame(const ame_track_params &t) {
     return c + (warm ? 26.0 : 0.0);                     // two table look-ups + the 2x2 mix in explicit FP64 ops
 }
 
-// k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes tracks would run
-// both variants one after the other.  Every track therefore gets a whole number of warps, in proportion to its
-// cost (frames x cost per frame), and its 32 * warps jobs are spread over its chunks by length.
-std::vector<int> eq_warps_per_track(const std::vector<std::vector<int64_t>> &chunks, const std::vector<double> &cost,
-                                    int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
+// k_eq runs one thread per tile and switches on the track's variant, so a warp that mixes VARIANTS would run
+// both one after the other; tracks of the same variant can share a warp (coefficients are per-thread registers).
+// Every track gets a number of jobs (threads) in proportion to its cost (frames x cost per frame); the jobs of a
+// wave are then laid out variant by variant and only the end of each variant's run is padded to a whole warp.
+// (Until late in round 2 every track got whole WARPS: with ~9 warps per track the rounding left the cheapest
+// tracks of a 128-track launch with 14 % more work per thread than the mean, and the launch ended with them.)
+int eq_variant_of(const ame_track_params &t) {
+    int variant = 0;
+    for (int s = 0; s < 4; ++s)
+        if (t.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
+    if (t.flags & AME_F_WARMTH) variant |= 16;
+    return variant;
+}
+
+std::vector<int64_t> eq_jobs_per_track(const ame_track_params *tracks, const std::vector<std::vector<int64_t>> &chunks,
+                                       const std::vector<double> &cost, int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
     const int n = (int)chunks.size();
-    std::vector<int> warps(n, 0);
+    std::vector<int64_t> jobs(n, 0), cap(n, 0), floor_jobs(n, 0);
     std::vector<double> weight(n, 0.0);
-    std::vector<int> cap(n, 0);
     double wsum = 0;
+    unsigned variants = 0;
+    int n_variants = 0;
     for (int t = t_lo; t < t_hi; ++t) {
         int64_t frames = 0, max_jobs = 0;
         for (int64_t c : chunks[t]) { frames += c; max_jobs += std::max<int64_t>(1, c / min_tile); }
         weight[t] = (double)frames * cost[t];
-        cap[t] = (int)std::max<int64_t>(1, (max_jobs + 31) / 32);
+        cap[t] = std::max<int64_t>(1, max_jobs);
+        floor_jobs[t] = std::max<int64_t>(1, (int64_t)chunks[t].size());      // tile_jobs makes one job per chunk at least
         wsum += weight[t];
+        const unsigned bit = 1u << eq_variant_of(tracks[t]);
+        if (!(variants & bit)) { variants |= bit; ++n_variants; }
     }
-    int64_t avail = std::max<int64_t>(t_hi - t_lo, slots / 32);
+    // threads to hand out: the resident set minus the padding at the end of every variant's run
+    int64_t avail = std::max<int64_t>(32 * (int64_t)(t_hi - t_lo), slots) - 31 * (int64_t)n_variants;
     std::vector<std::pair<double, int>> rem;
     int64_t used = 0;
     for (int t = t_lo; t < t_hi; ++t) {
-        const double share = wsum > 0 ? avail * weight[t] / wsum : 1.0;
-        warps[t] = std::min(cap[t], std::max(1, (int)share));
-        used += warps[t];
-        rem.emplace_back(share - warps[t], t);
+        const double share = wsum > 0 ? (double)avail * weight[t] / wsum : 32.0;
+        jobs[t] = std::min(cap[t], std::max(floor_jobs[t], (int64_t)share));
+        used += jobs[t];
+        rem.emplace_back(share - (double)jobs[t], t);
     }
     std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
     for (size_t i = 0; i < rem.size() && used < avail; ++i)
-        if (warps[rem[i].second] < cap[rem[i].second]) { ++warps[rem[i].second]; ++used; }
-    return warps;
+        if (jobs[rem[i].second] < cap[rem[i].second]) { ++jobs[rem[i].second]; ++used; }
+    return jobs;
 }
 
 int validate(const ame_track_params &t, int idx) {
@@ -775,7 +791,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
     constexpr int64_t kMinTile = 512;
     int64_t split_tile = kMinTile;
     std::vector<double> eq_cost(n_tracks);
-    std::vector<int> eq_warps(n_tracks, 1);
+    std::vector<int64_t> eq_want(n_tracks, 32);
     int max_warm_kw = 0, min_s100 = 1 << 30;
     for (int t = 0; t < n_tracks; ++t) {
         eq_cost[t] = eq_cost_per_frame(p->tracks[t]);
@@ -806,9 +822,9 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             }
         }
         split_tile = std::max(split_tile, pick_tile(cm, fewer_threads(split_slots, mb_fr, mb_warm), kMinTile));
-        const std::vector<int> tw = eq_warps_per_track(chunks_all, eq_cost, wv.track_lo, wv.track_hi,
-                                                       fewer_threads(eq_slots, eq_frames, eq_warm), kMinTile);
-        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_warps[t] = tw[t];
+        const std::vector<int64_t> tw = eq_jobs_per_track(p->tracks.data(), chunks_all, eq_cost, wv.track_lo, wv.track_hi,
+                                                          fewer_threads(eq_slots, eq_frames, eq_warm), kMinTile);
+        for (int t = wv.track_lo; t < wv.track_hi; ++t) eq_want[t] = tw[t];
     }
     p->eq_tile = 0;
     p->split_tile = o.xover_tile_frames > 0 ? (int)align_up(o.xover_tile_frames, 8) : (int)split_tile;
@@ -842,12 +858,10 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
         wv.lim_lo = (int)lim_jobs.size();
         wv.seg_lo = n_seg_total;
         int64_t n_groups = 0;                          // group records of this wave (slot-local indices)
+        std::map<int, std::vector<TileJob>> eq_bucket;   // k_eq jobs of this wave by variant (a warp runs ONE variant)
         for (int t = wv.track_lo; t < wv.track_hi; ++t) {
             ame_track_params &tp = p->tracks[t];
-            int variant = 0;
-            for (int s = 0; s < 4; ++s)
-                if (tp.eq[s].kind != AME_EQ_BYPASS) variant |= 1 << s;
-            if (tp.flags & AME_F_WARMTH) variant |= 16;
+            const int variant = eq_variant_of(tp);
             const bool mb = (tp.flags & AME_F_MULTIBAND) != 0;
             if (mb) {
                 mb_delta[t] = p->mb_offset[t] - tp.offset_frames;
@@ -866,28 +880,30 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                     }
                 }
             }
-            // k_eq jobs of this track: 32 * warps jobs spread over the chunks by length (or the requested tile)
-            const size_t eq_first = eq_jobs.size();
+            // k_eq jobs of this track: eq_want[t] jobs spread over the chunks by length (or the requested tile), collected
+            // per variant and laid out at the end of the wave
             {
-                int64_t c0e = 0;
-                const int64_t want = (int64_t)eq_warps[t] * 32;
+                std::vector<TileJob> &bucket = eq_bucket[variant];
+                int64_t c0e = 0, jobs_before = 0;
+                int64_t nf = 0;
+                for (int64_t cn : chunks_all[t]) nf += cn;
+                nf = std::max<int64_t>(nf, 1);
+                const int64_t want = eq_want[t];
                 for (int64_t cn : chunks_all[t]) {
                     const int64_t cb = tp.offset_frames + tp.halo_frames + c0e, ce = cb + cn;
                     int64_t T;
                     if (o.eq_tile_frames > 0) {
                         T = align_up(o.eq_tile_frames, 8);
                     } else {
-                        const int64_t jc = std::max<int64_t>(1, want * cn / std::max<int64_t>(tp.n_frames, 1));   // floor: never over `want`
+                        // cumulative rounding: the chunks together get exactly `want` jobs (never more)
+                        const int64_t upto = (int64_t)((__int128)want * (c0e + cn) / nf);
+                        const int64_t jc = std::max<int64_t>(1, upto - jobs_before);
+                        jobs_before = upto;
                         T = std::max<int64_t>(kMinTile, align_up((cn + jc - 1) / jc, 8));
                     }
-                    tile_jobs(eq_jobs, t, variant, cb, ce, T);
+                    tile_jobs(bucket, t, variant, cb, ce, T);
                     p->eq_tile = std::max<int>(p->eq_tile, (int)std::min<int64_t>(T, INT32_MAX));
                     c0e += cn;
-                }
-                if (eq_jobs.size() > eq_first) {            // whole warps per track: pad with empty jobs
-                    TileJob d = eq_jobs.back();
-                    d.tile_begin = d.tile_end;
-                    while ((eq_jobs.size() - eq_first) % 32) eq_jobs.push_back(d);
                 }
             }
             int64_t c0 = 0;
@@ -956,6 +972,25 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             const ChainJob &cj = chain_jobs[c];
             for (int64_t tb = 0; tb < cj.n; tb += kWfTile)
                 wf_jobs.push_back(WfJob{tb, (int64_t)cj.band * p->mb_frames + cj.mb_begin, cj.n, cj.grp_begin, c, cj.look, cj.thr_i, cj.tile0});
+        }
+        {   // every variant's run is padded to whole warps (a warp runs ONE variant); the warps of the variants are then
+            // interleaved in proportion, so that every CTA - hence every SM - holds the wave's mix of FP64-heavy and
+            // load-bound variants instead of some SMs running only 4-stage cascades and others only conversions
+            std::vector<std::pair<double, std::pair<int, int>>> order;     // (position in [0, 1), (variant, warp of the variant))
+            for (auto &kv : eq_bucket) {
+                std::vector<TileJob> &b = kv.second;
+                if (b.empty()) continue;
+                TileJob d = b.back();
+                d.tile_begin = d.tile_end;
+                while (b.size() % 32) b.push_back(d);
+                const int nw = (int)(b.size() / 32);
+                for (int w = 0; w < nw; ++w) order.push_back({(w + 0.5) / nw, {kv.first, w}});
+            }
+            if (!std::getenv("AME_EQ_SORTED")) std::stable_sort(order.begin(), order.end());      // experiments: variant by variant
+            for (const auto &o2 : order) {
+                const std::vector<TileJob> &b = eq_bucket[o2.second.first];
+                eq_jobs.insert(eq_jobs.end(), b.begin() + (size_t)o2.second.second * 32, b.begin() + (size_t)o2.second.second * 32 + 32);
+            }
         }
         wv.eq_n = (int)eq_jobs.size() - wv.eq_lo; wv.split_n = (int)split_jobs.size() - wv.split_lo;
         wv.chain_n = (int)chain_jobs.size() - wv.chain_lo; wv.wf_n = (int)wf_jobs.size() - wv.wf_lo;
