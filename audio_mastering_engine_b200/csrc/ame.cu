@@ -306,6 +306,14 @@ int eq_variant_of(const ame_track_params &t) {
     return variant;
 }
 
+inline int eq_block() {          // 8 warps in ONE CTA per SM (experiments: AME_EQ_BLOCK=128 = two 4-warp CTAs)
+    static const int b = [] { const char *e = std::getenv("AME_EQ_BLOCK"); return (e && std::atoi(e) == 128) ? 128 : 256; }();
+    return b;
+}
+
+// Threads handed out = the resident set minus the padding at the end of every variant's run (a warp).  Padding the runs to
+// whole 8-warp CTAs (no CTA would mix two variants) was measured too: 9.84 ms against 9.69 ms on the 128-track launch -
+// the ~4 % of idle threads cost more than the ~12 mixed CTAs.
 std::vector<int64_t> eq_jobs_per_track(const ame_track_params *tracks, const std::vector<std::vector<int64_t>> &chunks,
                                        const std::vector<double> &cost, int t_lo, int t_hi, int64_t slots, int64_t min_tile) {
     const int n = (int)chunks.size();
@@ -324,8 +332,7 @@ std::vector<int64_t> eq_jobs_per_track(const ame_track_params *tracks, const std
         const unsigned bit = 1u << eq_variant_of(tracks[t]);
         if (!(variants & bit)) { variants |= bit; ++n_variants; }
     }
-    // threads to hand out: the resident set minus the padding at the end of every variant's run
-    int64_t avail = std::max<int64_t>(32 * (int64_t)(t_hi - t_lo), slots) - 31 * (int64_t)n_variants;
+    const int64_t avail = std::max<int64_t>(32 * (int64_t)(t_hi - t_lo), slots) - 31 * (int64_t)n_variants;
     std::vector<std::pair<double, int>> rem;
     int64_t used = 0;
     for (int t = t_lo; t < t_hi; ++t) {
@@ -465,7 +472,7 @@ int run_eq(ame_plan *p, const Wave &w, const int16_t *d_in, int16_t *d_pre, cuda
     if (p->precision == 1)
         k_eq_f32<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
     else
-        k_eq<<<(w.eq_n + 127) / 128, 128, 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
+        k_eq<<<(w.eq_n + eq_block() - 1) / eq_block(), eq_block(), 0, s>>>(p->d_eq_jobs + w.eq_lo, w.eq_n, p->d_tracks, p->d_luts, d_in, d_pre);
     LAUNCH_CHECK(p);
     t_end(p, S_EQ, s);
     return AME_OK;
@@ -973,9 +980,11 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
             for (int64_t tb = 0; tb < cj.n; tb += kWfTile)
                 wf_jobs.push_back(WfJob{tb, (int64_t)cj.band * p->mb_frames + cj.mb_begin, cj.n, cj.grp_begin, c, cj.look, cj.thr_i, cj.tile0});
         }
-        {   // every variant's run is padded to whole warps (a warp runs ONE variant); the warps of the variants are then
-            // interleaved in proportion, so that every CTA - hence every SM - holds the wave's mix of FP64-heavy and
-            // load-bound variants instead of some SMs running only 4-stage cascades and others only conversions
+        {   // every variant's run is padded to whole warps (a warp runs ONE variant) and the runs follow one another; with one
+            // 8-warp CTA per SM nearly every SM then executes ONE variant - each variant is its own ~19 KB unrolled loop in
+            // the instruction cache (two 4-warp CTAs of different variants per SM: 10.5 ms on the 128-track launch, one 8-warp
+            // CTA: 9.7 ms).  Interleaving the variants' warps in proportion (every SM gets the wave's mix of FP64-heavy and
+            // load-bound warps; AME_EQ_INTERLEAVE) gave 18.0 ms: four loops per CTA (profiles/r02/summary.md).
             std::vector<std::pair<double, std::pair<int, int>>> order;     // (position in [0, 1), (variant, warp of the variant))
             for (auto &kv : eq_bucket) {
                 std::vector<TileJob> &b = kv.second;
@@ -986,7 +995,7 @@ int ame_plan_create(int device, const ame_track_params *tracks, int32_t n_tracks
                 const int nw = (int)(b.size() / 32);
                 for (int w = 0; w < nw; ++w) order.push_back({(w + 0.5) / nw, {kv.first, w}});
             }
-            if (!std::getenv("AME_EQ_SORTED")) std::stable_sort(order.begin(), order.end());      // experiments: variant by variant
+            if (std::getenv("AME_EQ_INTERLEAVE")) std::stable_sort(order.begin(), order.end());   // experiment (see above): lost
             for (const auto &o2 : order) {
                 const std::vector<TileJob> &b = eq_bucket[o2.second.first];
                 eq_jobs.insert(eq_jobs.end(), b.begin() + (size_t)o2.second.second * 32, b.begin() + (size_t)o2.second.second * 32 + 32);

@@ -304,7 +304,7 @@ __device__ __forceinline__ void eq_tile(const TileJob &job, const ame_track_para
 }
 
 #define AME_EQ_KERNEL(NAME, F, SK)                                                                                  \
-__global__ void __launch_bounds__(128, 2)                                                                          \
+__global__ void __launch_bounds__(256, 1)                                                                          \
 NAME(const TileJob *__restrict__ jobs, int n_jobs, const ame_track_params *__restrict__ tracks,                    \
      const double *__restrict__ luts, const int16_t *__restrict__ in, int16_t *__restrict__ pre) {                 \
     const int j = blockIdx.x * blockDim.x + threadIdx.x;                                                           \
